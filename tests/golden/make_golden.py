@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by RUNNING THE REFERENCE ITSELF in this container.
+
+The reference ships no tests or golden vectors, so the pins are
+outputs of its own unmodified sources (/root/reference/code/MPI/*.cc, compiled by
+oracle/Makefile into oracle/_ref/ against the stand-in mpi.h/cblas.h) with a real
+OpenBLAS 0.3.15 behind cblas_* ("openblas") and with plain left-to-right loops ("naive").
+Run from the repo root:   python tests/golden/make_golden.py
+Needs /root/reference (to build oracle/_ref); the produced fixtures are committed so the
+tests never need it.
+
+Each fixture holds: n, max_iter, k (the integer printed in "[STEP k]"), the r'r history
+(one value per executed loop index), final x, and the numbers of the DEBUG line
+(cg.cc:152-153).
+"""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import oracle as O  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+OUT = os.path.dirname(os.path.abspath(__file__))
+LINE = re.compile(r"\[STEP (\d+)\] residual = (\S+), \|\|x\|\| = (\S+), \|\|Ax - b\|\|/\|\|b\|\| = (\S+)")
+
+
+def run_ref(args, blas, tail=(), threads=8):
+    """args + [results file] + tail: `cgsolver N outfile [max_iter]` puts the outfile second."""
+    with tempfile.TemporaryDirectory() as td:
+        env = dict(os.environ, CGREF_BLAS=blas, CGREF_HIST=os.path.join(td, "hist"),
+                   CGREF_XOUT=os.path.join(td, "x"), OPENBLAS_NUM_THREADS=str(threads),
+                   OMP_NUM_THREADS=str(threads))
+        res = subprocess.run(list(args) + [os.path.join(td, "results.txt")] + list(tail), env=env,
+                             check=True, capture_output=True, text=True)
+        m = LINE.search(res.stdout)
+        assert m, res.stdout
+        hist = np.fromfile(os.path.join(td, "hist"), dtype=np.float64)
+        x = np.fromfile(os.path.join(td, "x"), dtype=np.float64)
+        row = open(os.path.join(td, "results.txt")).read().strip()
+    # ddot(v, v) log = [rsnew of every executed iteration ..., DEBUG r.r, b.b, x.x]
+    # (rsold at cg.cc:91 is ddot(r_sub, p_sub) on two different buffers: not logged)
+    return dict(k=int(m.group(1)), resid_print=float(m.group(2)), norm_x=float(m.group(3)),
+                rel_resid=float(m.group(4)), hist=hist[:-3], x=x, stdout_line=m.group(0),
+                results_row=row)
+
+
+def save(name, meta, runs):
+    d = dict(meta)
+    for blas, r in runs.items():
+        for key, v in r.items():
+            d[f"{blas}_{key}"] = v
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    for blas, r in runs.items():
+        print(f"{name:28s} {blas:9s} k={r['k']:5d} iters_logged={len(r['hist']):5d} "
+              f"||x||={r['norm_x']:.6e} relres={r['rel_resid']:.6e}")
+
+
+def main():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    gen = os.path.join(REF, "cgsolver_ref")
+    mtx = os.path.join(REF, "cgsolver_ref_mtx")
+    for n, max_iter in [(1024, None), (2048, None), (4096, None), (1448, 200), (1000, 50)]:
+        tail = [] if max_iter is None else [str(max_iter)]
+        runs = {blas: run_ref([gen, str(n)], blas, tail) for blas in ("openblas", "naive")}
+        name = f"gen_n{n}" + ("" if max_iter is None else f"_it{max_iter}")
+        save(name, dict(n=n, max_iter=n if max_iter is None else max_iter, kind="generate_lap2d"), runs)
+    with tempfile.TemporaryDirectory() as td:
+        for g in (30, 100):
+            path = os.path.join(td, f"lap2D_5pt_n{g}.mtx")
+            O.write_lap2d_5pt_mtx(path, g)
+            runs = {blas: run_ref([mtx, path], blas) for blas in ("openblas", "naive")}
+            save(f"mtx_lap2d_5pt_n{g}", dict(n=g * g, max_iter=g * g, kind="mtx", grid=g), runs)
+
+
+if __name__ == "__main__":
+    main()
