@@ -1,0 +1,902 @@
+// capi.cu -- the C ABI of include/cgb200.h: context management, the CG iteration schedule
+// (CUDA-graph replay, device-side convergence, batched host polling) and the NCCL gather.
+//
+// Multi-GPU design (replaces MPI_Allgatherv + 2 x MPI_Allreduce per iteration,
+// code/MPI/cg.cc:105-136): A is row-sharded by the reference's partition rule; the O(N) vectors
+// x, r, p are REPLICATED and updated redundantly by every rank, so the only exchange per
+// iteration is ONE all-gather of [Ap rows | p'Ap block partials] after the mat-vec
+// (ncclAllGather, in place).  The scalars (alpha, beta, r'r, the stop test) are then computed
+// by every rank from identical data in an identical order: bitwise equal on all ranks without
+// any all-reduce.
+#include "../../include/cgb200.h"
+#include "cgb_kernels.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace cgb;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver               \
+                            ? CGB_ERR_NO_DEVICE                                                    \
+                            : CGB_ERR_CUDA,                                                        \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------ NCCL, loaded on demand
+// (dlopen keeps libnccl out of DT_NEEDED: inside a torch process we bind to the copy torch
+// already loaded, in the C++ host program to the system one.)
+namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[CGB_UNIQUE_ID_BYTES]; } ncclUniqueId;
+enum { kNcclDouble = 8 };
+struct Nccl {
+    void *h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int *) = nullptr;
+};
+Nccl g_nccl;
+
+int load_nccl()
+{
+    if (g_nccl.h) return CGB_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(CGB_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    Nccl n;
+    n.h = h;
+    n.GetUniqueId = (decltype(n.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    n.CommInitRank = (decltype(n.CommInitRank))dlsym(h, "ncclCommInitRank");
+    n.CommDestroy = (decltype(n.CommDestroy))dlsym(h, "ncclCommDestroy");
+    n.AllGather = (decltype(n.AllGather))dlsym(h, "ncclAllGather");
+    n.GetErrorString = (decltype(n.GetErrorString))dlsym(h, "ncclGetErrorString");
+    n.GetVersion = (decltype(n.GetVersion))dlsym(h, "ncclGetVersion");
+    if (!n.GetUniqueId || !n.CommInitRank || !n.CommDestroy || !n.AllGather || !n.GetErrorString)
+        return fail(CGB_ERR_NCCL, "libnccl lacks a required symbol");
+    g_nccl = n;
+    return CGB_OK;
+}
+} // namespace
+
+#define NK(call)                                                                                   \
+    do {                                                                                           \
+        int r_ = (call);                                                                           \
+        if (r_ != 0)                                                                               \
+            return fail(CGB_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_));          \
+    } while (0)
+
+// ------------------------------------------------------------------ context
+struct cgb_ctx {
+    long long n = 0, ld = 0, rows = 0, row0 = 0, n_loc = 0, maxrows = 0, nchunks = 0;
+    int rank = 0, world = 1, device = 0, sm_count = 0;
+    int variant = 0, nblk = 0;
+    long long slot = 0, slot_cap = 0;
+    int opt_graph = 1, opt_profile = 0, opt_num_threads = 0, opt_block_width = 0, opt_transposed = 1;
+    int poll_every = 16, graph_unroll = 4;
+
+    double *A = nullptr, *p = nullptr, *r = nullptr, *x = nullptr, *b = nullptr;
+    double *apx = nullptr, *rrpart = nullptr, *scratch = nullptr, *hist = nullptr, *sink = nullptr;
+    long long hist_cap = 0;
+    State *st = nullptr;
+    int *h_done = nullptr, *d_hdone = nullptr; // mapped pinned flag
+    double *h_pin = nullptr;                   // pinned staging for small D2H reads
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_batch[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> prof_ev;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    ncclComm_t comm = nullptr;
+
+    bool matrix_set = false, rhs_set = false, in_solve = false;
+    long long max_iter = 0, launched = 0, kernel_launches = 0;
+    double tol = 1e-10, graph_tol = -1.0;
+    double loop_ms = 0.0;
+    double prof_gemv_ms = 0.0;
+    long long prof_gemv_n = 0;
+};
+
+namespace {
+
+int use_device(cgb_ctx *c)
+{
+    if (!c) return fail(CGB_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    return CGB_OK;
+}
+
+Gather make_gather(const cgb_ctx *c)
+{
+    Gather g;
+    g.n_loc = c->n_loc > 0 ? c->n_loc : 1;
+    g.slot = c->slot;
+    g.maxrows = c->maxrows;
+    g.world = c->world;
+    g.nblk = c->nblk;
+    return g;
+}
+
+GemvArgs make_gemv_args(const cgb_ctx *c, const double *v, int advance)
+{
+    GemvArgs a;
+    memset(&a, 0, sizeof a);
+    a.A = c->A;
+    a.v = v;
+    a.out = c->apx + (long long)c->rank * c->slot;
+    a.npeers = 0;
+    a.ld = c->ld;
+    a.rows = c->rows;
+    a.row0 = c->row0;
+    a.maxrows = c->maxrows;
+    a.st = c->st;
+    a.rrpart = c->rrpart;
+    a.nchunks = c->nchunks;
+    a.hist = c->hist;
+    a.advance = advance;
+    return a;
+}
+
+VecArgs make_vec_args(const cgb_ctx *c)
+{
+    VecArgs a;
+    memset(&a, 0, sizeof a);
+    a.x = c->x;
+    a.r = c->r;
+    a.p = c->p;
+    a.b = c->b;
+    a.apx = c->apx;
+    a.rrpart = c->rrpart;
+    a.st = c->st;
+    a.host_done = c->d_hdone;
+    a.hist = c->hist;
+    a.g = make_gather(c);
+    a.n = c->n;
+    a.tol = c->tol;
+    return a;
+}
+
+void set_variant(cgb_ctx *c, int v)
+{
+    c->variant = v;
+    c->nblk = c->sm_count * gemv_variant(v).ctas_per_sm;
+    c->slot = (c->maxrows + c->nblk + 1) & ~1LL;
+}
+
+void drop_graph(cgb_ctx *c)
+{
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    c->graph_exec = nullptr;
+    c->graph = nullptr;
+}
+
+// the mat-vec and, for world > 1, the gather of its result
+int launch_matvec(cgb_ctx *c, const double *v, int advance, int variant)
+{
+    const GemvArgs a = make_gemv_args(c, v, advance);
+    CK(gemv_variant(variant).launch(a, c->sm_count * gemv_variant(variant).ctas_per_sm, c->stream));
+    c->kernel_launches += 1;
+    return CGB_OK;
+}
+
+int launch_gather(cgb_ctx *c)
+{
+    if (c->world == 1) return CGB_OK;
+    if (!c->comm) return fail(CGB_ERR_STATE, "world > 1 but cgb_comm_init was not called");
+    NK(g_nccl.AllGather(c->apx + (long long)c->rank * c->slot, c->apx, (size_t)c->slot, kNcclDouble,
+                        c->comm, c->stream));
+    return CGB_OK;
+}
+
+int launch_iteration(cgb_ctx *c)
+{
+    int rc = launch_matvec(c, c->p, 1, c->variant);                        // cg.cc:100-102
+    if (rc) return rc;
+    if ((rc = launch_gather(c))) return rc;                                 // cg.cc:135-136 (moved)
+    const VecArgs va = make_vec_args(c);
+    CK(launch_update_xr(va, c->stream));                                    // cg.cc:105-117
+    CK(launch_update_p(va, c->stream));                                     // cg.cc:120-132
+    c->kernel_launches += 2;
+    return CGB_OK;
+}
+
+int build_graph(cgb_ctx *c)
+{
+    drop_graph(c);
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = CGB_OK;
+    const long long before = c->kernel_launches;
+    for (int u = 0; u < c->graph_unroll && rc == CGB_OK; ++u) rc = launch_iteration(c);
+    c->kernel_launches = before; // capture launches nothing
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (rc != CGB_OK) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+    }
+    CK(e);
+    c->graph = g;
+    CK(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
+    c->graph_tol = c->tol; // tol and the history pointer are baked into the captured arguments
+    return CGB_OK;
+}
+
+int read_state(cgb_ctx *c, State *out)
+{
+    CK(cudaMemcpyAsync(out, c->st, sizeof(State), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return CGB_OK;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------ library
+extern "C" int cgb_abi_version(void) { return CGB_ABI_VERSION; }
+extern "C" const char *cgb_last_error(void) { return g_err; }
+
+extern "C" int cgb_device_count(int *count)
+{
+    if (!count) return fail(CGB_ERR_INVALID, "null count");
+    *count = 0;
+    CK(cudaGetDeviceCount(count));
+    return CGB_OK;
+}
+
+extern "C" int cgb_partition(int64_t n, int psize, int64_t *start_rows, int64_t *num_rows)
+{
+    if (n < 0 || psize < 1 || !start_rows || !num_rows) return fail(CGB_ERR_INVALID, "bad partition arguments");
+    // partition_matrix, code/MPI/cg.cc:236-268
+    const int64_t n_loc = n / psize;
+    int64_t i0 = 0;
+    for (int r = 0; r < psize - 1; ++r) {
+        start_rows[r] = i0;
+        num_rows[r] = n_loc;
+        i0 += n_loc;
+    }
+    start_rows[psize - 1] = i0;
+    num_rows[psize - 1] = n - i0;
+    return CGB_OK;
+}
+
+extern "C" int cgb_gemv_variant_count(void) { return gemv_variant_count(); }
+extern "C" const char *cgb_gemv_variant_name(int v)
+{
+    return (v >= 0 && v < gemv_variant_count()) ? gemv_variant(v).name : nullptr;
+}
+
+// ------------------------------------------------------------------ context
+extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **out)
+{
+    if (!out) return fail(CGB_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (n < 1) return fail(CGB_ERR_INVALID, "n must be >= 1 (got %lld)", (long long)n);
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
+        return fail(CGB_ERR_INVALID, "bad rank/world %d/%d (world <= %d)", rank, world, kMaxWorld);
+    if (n < world) return fail(CGB_ERR_INVALID, "n (%lld) < world (%d)", (long long)n, world);
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return fail(CGB_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(CGB_ERR_INVALID, "device %d out of range (%d)", device, ndev);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(CGB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+
+    cgb_ctx *c = new (std::nothrow) cgb_ctx;
+    if (!c) return fail(CGB_ERR_NOMEM, "out of host memory");
+    c->n = n;
+    c->ld = (n + 15) & ~15LL;
+    c->rank = rank;
+    c->world = world;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    std::vector<int64_t> start(world), num(world);
+    cgb_partition(n, world, start.data(), num.data());
+    c->row0 = start[rank];
+    c->rows = num[rank];
+    c->n_loc = n / world;
+    c->maxrows = num[world - 1];
+    c->nchunks = (n + kChunk - 1) / kChunk;
+    int max_cps = 1;
+    for (int v = 0; v < gemv_variant_count(); ++v)
+        if (gemv_variant(v).ctas_per_sm > max_cps) max_cps = gemv_variant(v).ctas_per_sm;
+    c->slot_cap = (c->maxrows + (long long)c->sm_count * max_cps + 1) & ~1LL;
+    set_variant(c, 0);
+
+    auto bail = [&](int code) {
+        cgb_destroy(c);
+        return code;
+    };
+#define CKB(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return bail(fail(e_ == cudaErrorMemoryAllocation ? CGB_ERR_NOMEM : CGB_ERR_CUDA,       \
+                             "%s failed: %s", #call, cudaGetErrorString(e_)));                     \
+    } while (0)
+    CKB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKB(cudaEventCreate(&c->ev0));
+    CKB(cudaEventCreate(&c->ev1));
+    CKB(cudaEventCreateWithFlags(&c->ev_batch[0], cudaEventDisableTiming));
+    CKB(cudaEventCreateWithFlags(&c->ev_batch[1], cudaEventDisableTiming));
+    const size_t vec_bytes = (size_t)c->ld * sizeof(double);
+    CKB(cudaMalloc(&c->A, (size_t)c->rows * c->ld * sizeof(double)));
+    CKB(cudaMalloc(&c->p, vec_bytes));
+    CKB(cudaMalloc(&c->r, vec_bytes));
+    CKB(cudaMalloc(&c->x, vec_bytes));
+    CKB(cudaMalloc(&c->b, vec_bytes));
+    CKB(cudaMalloc(&c->apx, (size_t)c->world * c->slot_cap * sizeof(double)));
+    CKB(cudaMalloc(&c->rrpart, (size_t)c->nchunks * sizeof(double)));
+    CKB(cudaMalloc(&c->scratch, (size_t)(3 * c->nchunks + 8) * sizeof(double)));
+    CKB(cudaMalloc(&c->sink, 64));
+    CKB(cudaMalloc(&c->st, sizeof(State)));
+    CKB(cudaHostAlloc(&c->h_done, sizeof(int), cudaHostAllocMapped));
+    CKB(cudaHostGetDevicePointer(&c->d_hdone, c->h_done, 0));
+    CKB(cudaHostAlloc(&c->h_pin, 64 * sizeof(double), cudaHostAllocDefault));
+    *c->h_done = 0;
+    CKB(cudaMemsetAsync(c->A, 0, (size_t)c->rows * c->ld * sizeof(double), c->stream));
+    CKB(cudaMemsetAsync(c->p, 0, vec_bytes, c->stream));
+    CKB(cudaMemsetAsync(c->r, 0, vec_bytes, c->stream));
+    CKB(cudaMemsetAsync(c->x, 0, vec_bytes, c->stream));
+    CKB(cudaMemsetAsync(c->b, 0, vec_bytes, c->stream));
+    CKB(cudaMemsetAsync(c->apx, 0, (size_t)c->world * c->slot_cap * sizeof(double), c->stream));
+    CKB(cudaMemsetAsync(c->rrpart, 0, (size_t)c->nchunks * sizeof(double), c->stream));
+    CKB(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
+    CKB(cudaStreamSynchronize(c->stream));
+#undef CKB
+    *out = c;
+    return CGB_OK;
+}
+
+extern "C" int cgb_destroy(cgb_ctx *c)
+{
+    if (!c) return CGB_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drop_graph(c);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    double *bufs[] = {c->A, c->p, c->r, c->x, c->b, c->apx, c->rrpart, c->scratch, c->hist, c->sink};
+    for (double *p : bufs)
+        if (p) cudaFree(p);
+    if (c->st) cudaFree(c->st);
+    if (c->h_done) cudaFreeHost(c->h_done);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->ev_batch)
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return CGB_OK;
+}
+
+extern "C" int cgb_comm_unique_id(void *id_out)
+{
+    if (!id_out) return fail(CGB_ERR_INVALID, "null id");
+    int rc = load_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return CGB_OK;
+}
+
+extern "C" int cgb_comm_init(cgb_ctx *c, const void *id_in)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (c->world == 1) return CGB_OK;
+    if (!id_in) return fail(CGB_ERR_INVALID, "null id");
+    if (c->comm) return fail(CGB_ERR_STATE, "communicator already initialised");
+    if ((rc = load_nccl())) return rc;
+    ncclUniqueId id;
+    memcpy(&id, id_in, sizeof id);
+    NK(g_nccl.CommInitRank(&c->comm, c->world, id, c->rank));
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------ inputs
+extern "C" int cgb_generate_lap2d(cgb_ctx *c)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
+    CK(launch_generate_lap2d(c->A, c->n, c->ld, c->row0, c->rows, c->stream));
+    c->kernel_launches += 1;
+    CK(cudaStreamSynchronize(c->stream));
+    c->matrix_set = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_set_matrix_rows(cgb_ctx *c, const double *rows_host, int64_t first_row,
+                                   int64_t nrows, int64_t ld_host)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
+    if (!rows_host || nrows < 0 || first_row < 0 || first_row + nrows > c->n || ld_host < c->n)
+        return fail(CGB_ERR_INVALID, "bad row block [%lld, +%lld) ld %lld", (long long)first_row,
+                    (long long)nrows, (long long)ld_host);
+    const long long lo = std::max<long long>(first_row, c->row0);
+    const long long hi = std::min<long long>(first_row + nrows, c->row0 + c->rows);
+    if (hi > lo) {
+        CK(cudaMemcpy2DAsync(c->A + (lo - c->row0) * c->ld, (size_t)c->ld * 8,
+                             rows_host + (lo - first_row) * ld_host, (size_t)ld_host * 8,
+                             (size_t)c->n * 8, (size_t)(hi - lo), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    c->matrix_set = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_set_matrix_coo(cgb_ctx *c, int64_t nz, const int32_t *irn, const int32_t *jcn,
+                                  const double *val, int symmetric)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
+    if (nz < 0 || (nz > 0 && (!irn || !jcn || !val))) return fail(CGB_ERR_INVALID, "bad COO arguments");
+    // Sequential "later entries overwrite" semantics (matrix.cc:12-21) under a parallel
+    // scatter: keep, for every destination cell, only the LAST entry that writes it.
+    std::unordered_map<long long, long long> last; // cell -> index of the last writer
+    last.reserve((size_t)nz * (symmetric ? 2 : 1));
+    for (long long z = 0; z < nz; ++z) {
+        const long long i = irn[z], j = jcn[z];
+        if (i < 0 || j < 0 || i >= c->n || j >= c->n)
+            return fail(CGB_ERR_INVALID, "COO entry %lld (%lld,%lld) outside %lld x %lld", z, i, j,
+                        c->n, c->n);
+        last[i * c->n + j] = z;
+        if (symmetric) last[j * c->n + i] = z;
+    }
+    // expand into plain (i, j, v) writes, at most one per cell
+    std::vector<int> ei, ej;
+    std::vector<double> ev;
+    ei.reserve(last.size());
+    ej.reserve(last.size());
+    ev.reserve(last.size());
+    for (const auto &kv : last) {
+        const long long i = kv.first / c->n, j = kv.first % c->n;
+        if (i < c->row0 || i >= c->row0 + c->rows) continue;
+        ei.push_back((int)i);
+        ej.push_back((int)j);
+        ev.push_back(val[kv.second]);
+    }
+    const long long m = (long long)ei.size();
+    CK(cudaMemsetAsync(c->A, 0, (size_t)c->rows * c->ld * sizeof(double), c->stream));
+    if (m > 0) {
+        int *di = nullptr, *dj = nullptr;
+        double *dv = nullptr;
+        CK(cudaMalloc(&di, m * sizeof(int)));
+        CK(cudaMalloc(&dj, m * sizeof(int)));
+        CK(cudaMalloc(&dv, m * sizeof(double)));
+        CK(cudaMemcpyAsync(di, ei.data(), m * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(dj, ej.data(), m * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(dv, ev.data(), m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CK(launch_scatter_coo(c->A, c->ld, c->row0, c->rows, di, dj, dv, m, 0, c->stream));
+        c->kernel_launches += 1;
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(di);
+        cudaFree(dj);
+        cudaFree(dv);
+    } else {
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    c->matrix_set = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_get_matrix_rows(cgb_ctx *c, double *rows_host, int64_t first_row, int64_t nrows,
+                                   int64_t ld_host)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (!rows_host || nrows < 0 || first_row < c->row0 || first_row + nrows > c->row0 + c->rows ||
+        ld_host < c->n)
+        return fail(CGB_ERR_INVALID, "rows [%lld, +%lld) are not inside this rank's shard",
+                    (long long)first_row, (long long)nrows);
+    if (nrows > 0) {
+        CK(cudaMemcpy2DAsync(rows_host, (size_t)ld_host * 8, c->A + (first_row - c->row0) * c->ld,
+                             (size_t)c->ld * 8, (size_t)c->n * 8, (size_t)nrows,
+                             cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return CGB_OK;
+}
+
+extern "C" int cgb_set_rhs(cgb_ctx *c, const double *b_host)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (!b_host) return fail(CGB_ERR_INVALID, "null b");
+    if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
+    CK(cudaMemcpyAsync(c->b, b_host, (size_t)c->n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->rhs_set = true;
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------ options
+extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
+{
+    if (!c || !key) return fail(CGB_ERR_INVALID, "null argument");
+    if (c->in_solve) return fail(CGB_ERR_STATE, "options cannot change during a solve");
+    const std::string k(key);
+    if (k == "gemv_variant") {
+        if (value < 0 || value >= gemv_variant_count())
+            return fail(CGB_ERR_INVALID, "gemv_variant %lld out of range", (long long)value);
+        set_variant(c, (int)value);
+        drop_graph(c);
+    } else if (k == "graph") {
+        c->opt_graph = value != 0;
+    } else if (k == "profile") {
+        c->opt_profile = value != 0;
+    } else if (k == "poll_every") {
+        if (value < 1) return fail(CGB_ERR_INVALID, "poll_every must be >= 1");
+        c->poll_every = (int)value;
+    } else if (k == "graph_unroll") {
+        if (value < 1 || value > 64) return fail(CGB_ERR_INVALID, "graph_unroll must be in [1, 64]");
+        c->graph_unroll = (int)value;
+        drop_graph(c);
+    } else if (k == "num_threads") {
+        c->opt_num_threads = (int)value;
+    } else if (k == "block_width") {
+        c->opt_block_width = (int)value;
+    } else if (k == "transposed") {
+        c->opt_transposed = value != 0;
+    } else {
+        return fail(CGB_ERR_INVALID, "unknown option '%s'", key);
+    }
+    return CGB_OK;
+}
+
+extern "C" int cgb_get_option(cgb_ctx *c, const char *key, int64_t *value)
+{
+    if (!c || !key || !value) return fail(CGB_ERR_INVALID, "null argument");
+    const std::string k(key);
+    if (k == "gemv_variant") *value = c->variant;
+    else if (k == "graph") *value = c->opt_graph;
+    else if (k == "profile") *value = c->opt_profile;
+    else if (k == "poll_every") *value = c->poll_every;
+    else if (k == "graph_unroll") *value = c->graph_unroll;
+    else if (k == "num_threads") *value = c->opt_num_threads;
+    else if (k == "block_width") *value = c->opt_block_width;
+    else if (k == "transposed") *value = c->opt_transposed;
+    else return fail(CGB_ERR_INVALID, "unknown option '%s'", key);
+    return CGB_OK;
+}
+
+extern "C" int cgb_get_layout(cgb_ctx *c, cgb_layout *out)
+{
+    if (!c || !out) return fail(CGB_ERR_INVALID, "null argument");
+    out->n = c->n;
+    out->ld = c->ld;
+    out->rows = c->rows;
+    out->row0 = c->row0;
+    out->rank = c->rank;
+    out->world = c->world;
+    out->device = c->device;
+    out->nblk = c->nblk;
+    out->sm_count = c->sm_count;
+    out->nchunks = c->nchunks;
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------ solve
+extern "C" int cgb_solve_begin(cgb_ctx *c, const double *x0_host, int64_t max_iter, double tol,
+                               int keep_history)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (!c->matrix_set) return fail(CGB_ERR_STATE, "matrix not set");
+    if (!c->rhs_set) return fail(CGB_ERR_STATE, "right-hand side not set");
+    if (c->in_solve) return fail(CGB_ERR_STATE, "solve already in progress");
+    if (max_iter < 0) return fail(CGB_ERR_INVALID, "max_iter < 0");
+    if (c->world > 1 && !c->comm) return fail(CGB_ERR_STATE, "world > 1 but cgb_comm_init was not called");
+    c->max_iter = max_iter;
+    c->tol = tol;
+    if (c->graph_exec && c->graph_tol != tol) drop_graph(c);
+    c->launched = 0;
+    c->loop_ms = 0.0;
+    c->prof_gemv_ms = 0.0;
+    c->prof_gemv_n = 0;
+    if (keep_history) {
+        const long long need = max_iter > 0 ? max_iter : 1;
+        if (need > c->hist_cap) {
+            if (c->hist) cudaFree(c->hist);
+            c->hist = nullptr;
+            c->hist_cap = 0;
+            CK(cudaMalloc(&c->hist, (size_t)need * sizeof(double)));
+            c->hist_cap = need;
+            drop_graph(c); // the history pointer is baked into captured kernel arguments
+        }
+        CK(cudaMemsetAsync(c->hist, 0, (size_t)c->hist_cap * sizeof(double), c->stream));
+    } else if (c->hist) {
+        cudaFree(c->hist);
+        c->hist = nullptr;
+        c->hist_cap = 0;
+        drop_graph(c);
+    }
+    State s0;
+    memset(&s0, 0, sizeof s0);
+    s0.iter = -1;
+    *c->h_done = 0;
+    CK(cudaMemcpyAsync(c->st, &s0, sizeof s0, cudaMemcpyHostToDevice, c->stream));
+    if (x0_host) CK(cudaMemcpyAsync(c->x, x0_host, (size_t)c->n * 8, cudaMemcpyHostToDevice, c->stream));
+    else CK(cudaMemsetAsync(c->x, 0, (size_t)c->ld * 8, c->stream));
+    // r = b - A x0 ; p = r ; partials of r.p                          cg.cc:77-92
+    if ((rc = launch_matvec(c, c->x, 0, c->variant))) return rc;
+    if ((rc = launch_gather(c))) return rc;
+    CK(launch_init_residual(make_vec_args(c), c->stream));
+    c->kernel_launches += 1;
+    CK(cudaStreamSynchronize(c->stream));
+    c->in_solve = true;
+    return CGB_OK;
+}
+
+extern "C" int cgb_iterate(cgb_ctx *c, int64_t iters, float *ms)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (!c->in_solve) return fail(CGB_ERR_STATE, "cgb_solve_begin was not called");
+    if (iters < 0) return fail(CGB_ERR_INVALID, "iters < 0");
+    long long todo = std::min<long long>(iters, c->max_iter - c->launched);
+    if (todo < 0) todo = 0;
+    const bool profile = c->opt_profile != 0;
+    const bool graph = c->opt_graph != 0 && !profile;
+    if (graph && !c->graph_exec && todo >= c->graph_unroll) {
+        if ((rc = build_graph(c))) return rc;
+    }
+    if (profile) {
+        while ((long long)c->prof_ev.size() < 2 * todo) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            c->prof_ev.push_back(e);
+        }
+    }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    long long issued = 0;
+    int batch_idx = 0;
+    while (issued < todo) {
+        if (*(volatile int *)c->h_done) break; // converged: later launches would be no-ops
+        const long long batch = std::min<long long>(c->poll_every, todo - issued);
+        long long i = 0;
+        while (i < batch) {
+            if (graph && c->graph_exec && batch - i >= c->graph_unroll) {
+                CK(cudaGraphLaunch(c->graph_exec, c->stream));
+                c->kernel_launches += 3LL * c->graph_unroll;
+                i += c->graph_unroll;
+            } else if (profile) {
+                const long long slot = 2 * (issued + i);
+                CK(cudaEventRecord(c->prof_ev[slot], c->stream));
+                if ((rc = launch_matvec(c, c->p, 1, c->variant))) return rc;
+                CK(cudaEventRecord(c->prof_ev[slot + 1], c->stream));
+                if ((rc = launch_gather(c))) return rc;
+                const VecArgs va = make_vec_args(c);
+                CK(launch_update_xr(va, c->stream));
+                CK(launch_update_p(va, c->stream));
+                c->kernel_launches += 2;
+                i += 1;
+            } else {
+                if ((rc = launch_iteration(c))) return rc;
+                i += 1;
+            }
+        }
+        issued += batch;
+        // keep at most two batches in flight so the host never runs far ahead of the stop flag
+        CK(cudaEventRecord(c->ev_batch[batch_idx & 1], c->stream));
+        if (batch_idx >= 1) CK(cudaEventSynchronize(c->ev_batch[(batch_idx - 1) & 1]));
+        ++batch_idx;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    c->loop_ms += t;
+    c->launched += issued;
+    if (profile) {
+        for (long long k = 0; k < issued; ++k) {
+            float g = 0.f;
+            CK(cudaEventElapsedTime(&g, c->prof_ev[2 * k], c->prof_ev[2 * k + 1]));
+            c->prof_gemv_ms += g;
+        }
+        c->prof_gemv_n += issued;
+    }
+    if (ms) *ms = t;
+    return CGB_OK;
+}
+
+extern "C" int cgb_solve_end(cgb_ctx *c, double *x_host, double *resid_hist, cgb_solve_info *info)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (!c->in_solve) return fail(CGB_ERR_STATE, "no solve in progress");
+    CK(launch_finalize(make_vec_args(c), c->stream));
+    c->kernel_launches += 1;
+    State s;
+    if ((rc = read_state(c, &s))) return rc;
+    if (x_host) CK(cudaMemcpyAsync(x_host, c->x, (size_t)c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+    const long long executed = s.done ? s.iter + 1 : s.iter;
+    if (resid_hist) {
+        if (!c->hist) return fail(CGB_ERR_STATE, "history was not requested in cgb_solve_begin");
+        if (executed > 0)
+            CK(cudaMemcpyAsync(resid_hist, c->hist, (size_t)executed * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    if (info) {
+        info->k = s.iter;
+        info->converged = s.done;
+        info->rsold = s.rsold;
+        info->rsnew = s.rsnew;
+        info->seconds = c->loop_ms * 1e-3;
+        info->iterations = executed;
+    }
+    c->in_solve = false;
+    return CGB_OK;
+}
+
+extern "C" int cgb_solve(cgb_ctx *c, double *x_host, int64_t max_iter, double tol, double *resid_hist,
+                         cgb_solve_info *info)
+{
+    if (!x_host) return fail(CGB_ERR_INVALID, "null x");
+    int rc = cgb_solve_begin(c, x_host, max_iter, tol, resid_hist != nullptr);
+    if (rc) return rc;
+    rc = cgb_iterate(c, max_iter, nullptr);
+    if (rc) {
+        c->in_solve = false;
+        return rc;
+    }
+    return cgb_solve_end(c, x_host, resid_hist, info);
+}
+
+extern "C" int cgb_residual_check(cgb_ctx *c, double *norm_x, double *rel_resid)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
+    if (!c->matrix_set || !c->rhs_set) return fail(CGB_ERR_STATE, "matrix / right-hand side not set");
+    // `done` may still be raised from the solve: the DEBUG mat-vec must run regardless
+    CK(cudaMemsetAsync(&c->st->done, 0, sizeof(int), c->stream));
+    if ((rc = launch_matvec(c, c->x, 0, c->variant))) return rc;   // cg.cc:146-147
+    if ((rc = launch_gather(c))) return rc;
+    double *out = c->scratch + 3 * c->nchunks;
+    CK(launch_debug_norms(make_vec_args(c), c->scratch, out, c->stream));
+    c->kernel_launches += 2;
+    CK(cudaMemcpyAsync(c->h_pin, out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (norm_x) *norm_x = c->h_pin[0];
+    if (rel_resid) *rel_resid = c->h_pin[1];
+    return CGB_OK;
+}
+
+// ------------------------------------------------------------------ kernel-level hooks
+extern "C" int cgb_gemv(cgb_ctx *c, const double *v_host, double *y_host, double *block_partials,
+                        double *pAp)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
+    if (!c->matrix_set) return fail(CGB_ERR_STATE, "matrix not set");
+    if (!v_host) return fail(CGB_ERR_INVALID, "null v");
+    CK(cudaMemsetAsync(&c->st->done, 0, sizeof(int), c->stream));
+    CK(cudaMemcpyAsync(c->p, v_host, (size_t)c->n * 8, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = launch_matvec(c, c->p, 0, c->variant))) return rc;
+    if ((rc = launch_gather(c))) return rc;
+    const double *mine = c->apx + (long long)c->rank * c->slot;
+    if (y_host) CK(cudaMemcpyAsync(y_host, mine, (size_t)c->rows * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (block_partials)
+        CK(cudaMemcpyAsync(block_partials, mine + c->maxrows, (size_t)c->nblk * 8, cudaMemcpyDeviceToHost,
+                           c->stream));
+    if (pAp) {
+        double *out = c->scratch + 3 * c->nchunks;
+        CK(launch_sum_partials(c->apx, make_gather(c), out, c->stream));
+        c->kernel_launches += 1;
+        CK(cudaMemcpyAsync(c->h_pin, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    if (pAp) *pAp = c->h_pin[0];
+    return CGB_OK;
+}
+
+extern "C" int cgb_dot(cgb_ctx *c, const double *a_host, const double *b_host, double *result)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
+    if (!a_host || !b_host || !result) return fail(CGB_ERR_INVALID, "null argument");
+    CK(cudaMemcpyAsync(c->p, a_host, (size_t)c->n * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->r, b_host, (size_t)c->n * 8, cudaMemcpyHostToDevice, c->stream));
+    double *out = c->scratch + 3 * c->nchunks;
+    CK(launch_dot(c->p, c->r, c->n, c->scratch, out, c->stream));
+    c->kernel_launches += 2;
+    CK(cudaMemcpyAsync(c->h_pin, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *result = c->h_pin[0];
+    return CGB_OK;
+}
+
+extern "C" int cgb_bench_gemv(cgb_ctx *c, int variant, int reps, float *ms_avg)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
+    if (!c->matrix_set) return fail(CGB_ERR_STATE, "matrix not set");
+    if (variant < 0) variant = c->variant;
+    if (variant >= gemv_variant_count() || reps < 1) return fail(CGB_ERR_INVALID, "bad variant / reps");
+    CK(cudaMemsetAsync(&c->st->done, 0, sizeof(int), c->stream));
+    if ((rc = launch_matvec(c, c->p, 0, variant))) return rc; // warm-up
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i)
+        if ((rc = launch_matvec(c, c->p, 0, variant))) return rc;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    if (ms_avg) *ms_avg = t / reps;
+    return CGB_OK;
+}
+
+extern "C" int cgb_bench_read(cgb_ctx *c, int reps, float *ms_avg)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (reps < 1) return fail(CGB_ERR_INVALID, "reps < 1");
+    const long long nd = c->rows * c->ld;
+    CK(launch_read_stream(c->A, nd, c->sink, c->sm_count, c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i) CK(launch_read_stream(c->A, nd, c->sink, c->sm_count, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    c->kernel_launches += reps + 1;
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    if (ms_avg) *ms_avg = t / reps;
+    return CGB_OK;
+}
+
+extern "C" int cgb_last_gemv_timing(cgb_ctx *c, float *ms_avg, int64_t *launches)
+{
+    if (!c) return fail(CGB_ERR_INVALID, "null context");
+    if (ms_avg) *ms_avg = c->prof_gemv_n ? (float)(c->prof_gemv_ms / (double)c->prof_gemv_n) : 0.f;
+    if (launches) *launches = c->prof_gemv_n;
+    return CGB_OK;
+}
+
+extern "C" int cgb_launch_count(cgb_ctx *c, int64_t *launches)
+{
+    if (!c || !launches) return fail(CGB_ERR_INVALID, "null argument");
+    *launches = c->kernel_launches;
+    return CGB_OK;
+}

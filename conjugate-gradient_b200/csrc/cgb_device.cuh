@@ -1,0 +1,195 @@
+// cgb_device.cuh -- device-side building blocks shared by the sm_100a kernels:
+// mbarrier / bulk-copy (TMA) PTX wrappers, the deterministic reduction primitives whose
+// order oracle/cg_oracle.c mirrors, and the structs passed to the kernels.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cgb {
+
+constexpr double kNearZero = 1.0e-14; // NEARZERO, code/MPI/cg.cc:8, code/CUDA/cg.cu:11
+constexpr int kChunk = 256;           // elements per r'r chunk partial
+constexpr int kMaxWorld = 8;
+
+// Scalars that live on the device for the whole solve (no host round trip per iteration;
+// the reference computes alpha/beta on the host after blocking copies, cg.cu:231-269).
+struct State {
+    double rsold;   // reference's rsold (stale after a convergence break, as the DEBUG line prints)
+    double rsnew;   // last r'r
+    double conj;    // last p'Ap          (diagnostic)
+    double alpha;   // last step length   (diagnostic)
+    long long iter; // loop bodies completed without breaking == the reference's k
+    int done;       // sqrt(rsnew) < tol fired
+    int pad;
+};
+
+// Geometry of the gathered mat-vec result: rank g owns slot g of `slot` doubles,
+// [0, rows_g) = its Ap rows, [maxrows, maxrows + nblk) = its p'Ap block partials.
+struct Gather {
+    long long n_loc;   // rows of every rank but the last (N / world)
+    long long slot;    // doubles per rank slot
+    long long maxrows; // rows of the last rank (the largest shard)
+    int world;
+    int nblk;
+};
+
+struct GemvArgs {
+    const double *A;      // rows x ld shard, zero-padded columns
+    const double *v;      // input vector, ld doubles, zero-padded
+    double *out;          // this rank's slot of the gathered result
+    double *peer_out[kMaxWorld]; // P2P mode: the same slot in every peer's buffer (self included)
+    int npeers;           // 0 = local store only
+    long long ld;
+    long long rows;
+    long long row0;       // global index of the shard's first row (index into v)
+    long long maxrows;
+    // bookkeeping done by block 0 before streaming (see kernels.cu: advance_state)
+    State *st;
+    const double *rrpart;
+    long long nchunks;
+    double *hist;         // nullable
+    int advance;          // 1 inside the CG loop, 0 for the init / DEBUG mat-vecs
+};
+
+// ------------------------------------------------------------------ reductions
+__device__ __forceinline__ double shfl_xor_f64(double v, int m)
+{
+    return __shfl_xor_sync(0xffffffffu, v, m);
+}
+
+// butterfly over the 32 lanes: every lane ends with the same, order-specified sum
+__device__ __forceinline__ double warp_butterfly(double v)
+{
+    v = __dadd_rn(v, shfl_xor_f64(v, 16));
+    v = __dadd_rn(v, shfl_xor_f64(v, 8));
+    v = __dadd_rn(v, shfl_xor_f64(v, 4));
+    v = __dadd_rn(v, shfl_xor_f64(v, 2));
+    v = __dadd_rn(v, shfl_xor_f64(v, 1));
+    return v;
+}
+
+// det_sum: lane l adds v[l], v[l+32], ... in ascending order, then the butterfly.
+// Must be called by one full warp; `v` may be shared or global memory.
+__device__ __forceinline__ double warp_det_sum(const double *v, long long n, int lane)
+{
+    double s = 0.0;
+    for (long long t = lane; t < n; t += 32) s = __dadd_rn(s, v[t]);
+    return warp_butterfly(s);
+}
+
+// same, elements addressed through the gather layout (block partials of all ranks)
+__device__ __forceinline__ double warp_det_sum_partials(const double *apx, const Gather &g, int lane)
+{
+    double s = 0.0;
+    const int total = g.world * g.nblk;
+    for (int t = lane; t < total; t += 32) {
+        const int r = t / g.nblk, c = t - r * g.nblk;
+        s = __dadd_rn(s, apx[(long long)r * g.slot + g.maxrows + c]);
+    }
+    return warp_butterfly(s);
+}
+
+// chunk256: perfect xor tree over the 256 per-thread values of a 256-thread block.
+// Returns the total in every thread of warp 0; `wsum` is 8 doubles of shared memory.
+__device__ __forceinline__ double block_chunk256(double v, double *wsum, int tid)
+{
+    v = warp_butterfly(v);
+    if ((tid & 31) == 0) wsum[tid >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (tid < 32) {
+        t = (tid < 8) ? wsum[tid] : 0.0;
+        t = __dadd_rn(t, shfl_xor_f64(t, 4));
+        t = __dadd_rn(t, shfl_xor_f64(t, 2));
+        t = __dadd_rn(t, shfl_xor_f64(t, 1));
+    }
+    return t;
+}
+
+__device__ __forceinline__ long long gather_index(const Gather &g, long long i)
+{
+    long long r = i / g.n_loc;
+    if (r > g.world - 1) r = g.world - 1;
+    return r * g.slot + (i - r * g.n_loc);
+}
+
+// ------------------------------------------------------------------ mbarrier / TMA
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must fault the launch (trap), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// 1-D bulk copy global -> shared through the TMA unit, completion on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar,
+                                         uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// streaming 128-bit load that does not allocate in L1 (direct-load mat-vec variant)
+__device__ __forceinline__ double2 ldg_stream_f64x2(const double *p)
+{
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+} // namespace cgb

@@ -1,0 +1,60 @@
+// cgb_kernels.h -- host-callable launchers of the sm_100a kernels (gemv.cu, vec.cu).
+#pragma once
+
+#include "cgb_device.cuh"
+
+namespace cgb {
+
+// ---- mat-vec (gemv.cu) --------------------------------------------------------------
+struct GemvVariant {
+    const char *name;
+    int ctas_per_sm; // grid = sm_count * ctas_per_sm persistent CTAs (= p'Ap block partials)
+    int threads;
+    cudaError_t (*launch)(const GemvArgs &a, int nblk, cudaStream_t s);
+};
+int gemv_variant_count();
+const GemvVariant &gemv_variant(int i);
+cudaError_t launch_read_stream(const double *A, long long ndoubles, double *sink, int sm_count,
+                               cudaStream_t s);
+
+// ---- vector kernels (vec.cu) -------------------------------------------------------
+struct VecArgs {
+    double *x, *r, *p;       // full-length (ld) replicated work vectors
+    const double *b;
+    const double *apx;       // gathered mat-vec result (see Gather)
+    double *rrpart;          // nchunks chunk partials of r'r
+    State *st;
+    int *host_done;          // mapped pinned flag the host polls (nullable)
+    double *hist;            // nullable
+    Gather g;
+    long long n;
+    double tol;
+};
+// r = b - A x0 ; p = r ; rrpart = chunk partials of r.p             (cg.cc:77-92)
+cudaError_t launch_init_residual(const VecArgs &a, cudaStream_t s);
+// alpha = rsold / max(p'Ap, rsold*NEARZERO) ; x += alpha p ; r -= alpha Ap ; r'r partials
+//                                                                   (cg.cc:105-117)
+cudaError_t launch_update_xr(const VecArgs &a, cudaStream_t s);
+// rsnew = sum(partials) ; stop test ; beta = rsnew/rsold ; p = r + beta p   (cg.cc:120-129)
+cudaError_t launch_update_p(const VecArgs &a, cudaStream_t s);
+// after the last iteration: rsold = rsnew, iter += 1 when the loop did not break (cg.cc:132)
+cudaError_t launch_finalize(const VecArgs &a, cudaStream_t s);
+// DEBUG block (cg.cc:144-154): out[0] = ||x||, out[1] = ||Ax-b|| / ||b||, given apx = A x
+cudaError_t launch_debug_norms(const VecArgs &a, double *scratch /* 3*nchunks */, double *out,
+                               cudaStream_t s);
+// generic deterministic dot (tests): out[0] = a.b
+cudaError_t launch_dot(const double *a, const double *b, long long n, double *scratch, double *out,
+                       cudaStream_t s);
+// total of the block partials of all ranks (tests): out[0] = p'Ap
+cudaError_t launch_sum_partials(const double *apx, const Gather &g, double *out, cudaStream_t s);
+
+// ---- matrix construction (vec.cu) --------------------------------------------------
+// generate_lap2d_matrix (cg.cc:159-188) into the shard
+cudaError_t launch_generate_lap2d(double *A, long long n, long long ld, long long row0,
+                                  long long rows, cudaStream_t s);
+// COO scatter, entries [z0, z1) -- sequential semantics are kept by the caller (see capi.cu)
+cudaError_t launch_scatter_coo(double *A, long long ld, long long row0, long long rows,
+                               const int *irn, const int *jcn, const double *val, long long nz,
+                               int symmetric, cudaStream_t s);
+
+} // namespace cgb

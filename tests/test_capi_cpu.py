@@ -1,0 +1,77 @@
+"""CPU tests of the drop-in boundary: libcgb200.so loads, exports every symbol that
+include/cgb200.h declares, host-only logic works, and compute entry points FAIL LOUDLY
+without a GPU (there is no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "cgb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cgb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(cgb):
+    lib = cgb.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/cgb200.h but not exported"
+    bound = {s[0] for s in cgb.SIGNATURES}
+    assert set(declared) == bound, set(declared) ^ bound
+
+
+def test_abi_version_and_variants(cgb):
+    lib = cgb.load()
+    assert lib.cgb_abi_version() == 1
+    names = cgb.gemv_variants()
+    assert len(names) >= 4 and len(set(names)) == len(names)
+    assert lib.cgb_gemv_variant_name(-1) is None and lib.cgb_gemv_variant_name(999) is None
+
+
+def test_partition_is_the_reference_rule(cgb, O):
+    for n, p in [(10, 1), (10, 3), (40000, 8), (56569, 8), (7, 7), (1 << 33, 5)]:
+        assert cgb.partition(n, p) == O.partition(n, p)
+    with pytest.raises(cgb.CgbError):
+        cgb.partition(10, 0)
+
+
+def test_no_cpu_fallback(cgb):
+    """Without a CUDA device every compute entry point returns an error; nothing is computed
+    on the host."""
+    try:
+        ndev = cgb.device_count()
+    except cgb.CgbError as e:
+        ndev = 0
+        assert e.code == 3  # CGB_ERR_NO_DEVICE
+    if ndev > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(cgb.CgbError) as ei:
+        cgb.Context(128)
+    assert ei.value.code == 3
+    lib = cgb.load()
+    assert lib.cgb_solve(None, None, 1, 1e-10, None, None) != 0
+    assert b"null" in lib.cgb_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "conjugate-gradient_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "_build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".cc")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                for needle in ("cg_oracle", "import oracle", "oracle/", "/root/reference"):
+                    hits = [ln for ln in text.splitlines() if needle in ln
+                            and not ln.strip().startswith(("//", "#", "*", "/*"))]
+                    assert not hits, (f, needle, hits[:2])
+    for f in ("include/cgb200.h",):
+        assert "cg_oracle" not in open(os.path.join(ROOT, f)).read()
