@@ -1,0 +1,212 @@
+// cg_solver.cpp -- see cg_solver.hpp.
+#include "cg_solver.hpp"
+
+#include "../../include/cgb200.h"
+#include "matrix_coo.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include <mutex>
+#include <thread>
+
+namespace {
+
+[[noreturn]] void raise(const char *what, int rc)
+{
+    throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + cgb_last_error());
+}
+
+} // namespace
+
+CGSolver::CGSolver() = default;
+CGSolver::~CGSolver() { destroy_contexts(); }
+
+void CGSolver::destroy_contexts()
+{
+    for (cgb_ctx *c : m_ctx) cgb_destroy(c);
+    m_ctx.clear();
+    m_ctx_n = 0;
+    m_rhs_uploaded = false;
+}
+
+void CGSolver::set_devices(const std::vector<int> &devices)
+{
+    if (devices.empty()) throw std::runtime_error("set_devices: empty device list");
+    destroy_contexts();
+    m_devices = devices;
+}
+
+// Runs f(rank) for every rank, each on its own host thread when there are several GPUs (the
+// collective steps need all ranks in flight at once); rethrows the first failure.
+template <class F> void CGSolver::on_all_ranks(F &&f)
+{
+    const int G = psize();
+    if (G == 1) {
+        f(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::mutex mu;
+    std::string err;
+    for (int r = 0; r < G; ++r)
+        th.emplace_back([&, r] {
+            try {
+                f(r);
+            } catch (const std::exception &e) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (err.empty()) err = e.what();
+            }
+        });
+    for (auto &t : th) t.join();
+    if (!err.empty()) throw std::runtime_error(err);
+}
+
+void CGSolver::ensure_contexts(int64_t n)
+{
+    if (!m_ctx.empty() && m_ctx_n == n) return;
+    destroy_contexts();
+    const int G = psize();
+    m_ctx.assign(G, nullptr);
+    for (int r = 0; r < G; ++r) {
+        const int rc = cgb_create(n, r, G, m_devices[r], &m_ctx[r]);
+        if (rc) raise("cgb_create", rc);
+    }
+    m_ctx_n = n;
+    if (G > 1) { // replaces MPI_Init / MPI_COMM_WORLD (cg_main.cc:15-20)
+        char id[CGB_UNIQUE_ID_BYTES];
+        int rc = cgb_comm_unique_id(id);
+        if (rc) raise("cgb_comm_unique_id", rc);
+        on_all_ranks([&](int r) {
+            const int rc2 = cgb_comm_init(m_ctx[r], id);
+            if (rc2) raise("cgb_comm_init", rc2);
+        });
+    }
+    if (m_variant >= 0)
+        for (cgb_ctx *c : m_ctx) {
+            const int rc = cgb_set_option(c, "gemv_variant", m_variant);
+            if (rc) raise("cgb_set_option(gemv_variant)", rc);
+        }
+}
+
+void CGSolver::generate_lap2d_matrix(int size)
+{
+    m_m = size;
+    m_n = size;
+    m_maxIter = size; // cg.cc:170-172
+    ensure_contexts(size);
+    on_all_ranks([&](int r) {
+        const int rc = cgb_generate_lap2d(m_ctx[r]);
+        if (rc) raise("cgb_generate_lap2d", rc);
+    });
+}
+
+void CGSolver::read_matrix(const std::string &filename)
+{
+    MatrixCOO coo;
+    coo.read(filename); // exits like the reference on unreadable / unsupported files
+    m_m = coo.m();
+    m_n = coo.n();
+    m_maxIter = coo.n(); // cg.cu:236 loops to m_n
+    if (m_m != m_n) throw std::runtime_error("read_matrix: the solver needs a square matrix");
+    ensure_contexts(m_n);
+    on_all_ranks([&](int r) {
+        const int rc = cgb_set_matrix_coo(m_ctx[r], coo.nz(), coo.irn.data(), coo.jcn.data(),
+                                          coo.a.data(), coo.is_sym());
+        if (rc) raise("cgb_set_matrix_coo", rc);
+    });
+}
+
+void CGSolver::set_max_iter(int maxIter) { m_maxIter = maxIter; }
+
+void CGSolver::init_source_term(double h)
+{
+    m_b.resize(m_n);
+    for (int i = 0; i < m_n; i++) {
+        m_b[i] = -2. * i * M_PI * M_PI * std::sin(10. * M_PI * i * h) * std::sin(10. * M_PI * i * h);
+    }
+    m_rhs_uploaded = false;
+}
+
+void CGSolver::partition_matrix(int N, int psize, int start_rows[], int num_rows[])
+{
+    std::vector<int64_t> s(psize), c(psize);
+    const int rc = cgb_partition(N, psize, s.data(), c.data());
+    if (rc) raise("cgb_partition", rc);
+    for (int r = 0; r < psize; ++r) {
+        start_rows[r] = static_cast<int>(s[r]);
+        num_rows[r] = static_cast<int>(c[r]);
+    }
+}
+
+void CGSolver::run_solve(double *x, int64_t max_iter)
+{
+    if (m_ctx.empty()) throw std::runtime_error("solve: no matrix (call generate_lap2d_matrix / read_matrix)");
+    if ((int)m_b.size() != m_n) throw std::runtime_error("solve: no source term (call init_source_term)");
+    const int G = psize();
+    std::vector<cgb_solve_info> info(G);
+    std::vector<double> nx(G), rr(G);
+    std::vector<std::vector<double>> xs(G > 1 ? G : 0); // every rank returns the full x
+    on_all_ranks([&](int r) {
+        int rc;
+        if (!m_rhs_uploaded && (rc = cgb_set_rhs(m_ctx[r], m_b.data()))) raise("cgb_set_rhs", rc);
+        double *xr = x;
+        if (r > 0) {
+            xs[r].assign(x, x + m_n);
+            xr = xs[r].data();
+        }
+        if ((rc = cgb_solve(m_ctx[r], xr, max_iter, m_tolerance, nullptr, &info[r]))) raise("cgb_solve", rc);
+        // DEBUG block, inside the caller's timed region like the reference's (cg.cc:144-154)
+        if ((rc = cgb_residual_check(m_ctx[r], &nx[r], &rr[r]))) raise("cgb_residual_check", rc);
+    });
+    m_rhs_uploaded = true;
+    m_stats = Stats();
+    m_stats.k = info[0].k;
+    m_stats.iterations = info[0].iterations;
+    m_stats.converged = info[0].converged != 0;
+    m_stats.rsold = info[0].rsold;
+    m_stats.norm_x = nx[0];
+    m_stats.rel_resid = rr[0];
+    for (int r = 0; r < G; ++r) m_stats.loop_seconds = std::max(m_stats.loop_seconds, info[r].seconds);
+    int64_t v = 0;
+    cgb_get_option(m_ctx[0], "gemv_variant", &v);
+    m_stats.gemv_variant = cgb_gemv_variant_name((int)v);
+    if (!m_quiet) {
+        std::cout << "\t[STEP " << m_stats.k << "] residual = " << std::scientific << std::sqrt(m_stats.rsold)
+                  << ", ||x|| = " << m_stats.norm_x << ", ||Ax - b||/||b|| = " << m_stats.rel_resid
+                  << std::endl;
+    }
+}
+
+void CGSolver::solve(std::vector<double> &x)
+{
+    if ((int)x.size() != m_n) throw std::runtime_error("solve: x has the wrong length");
+    run_solve(x.data(), m_maxIter);
+}
+
+int gemv_variant_for(int NUM_THREADS, int BLOCK_WIDTH)
+{
+    // consumer warps per CTA from NUM_THREADS, column tile from BLOCK_WIDTH; the names are the
+    // ones cgb_gemv_variant_name() reports
+    const char *want;
+    if (BLOCK_WIDTH <= 256) want = (NUM_THREADS <= 288) ? "tma_w8r2c256s6" : "tma_w8r4c256s3";
+    else if (NUM_THREADS <= 160) want = "tma_w4r4c512s3";
+    else if (NUM_THREADS <= 288) want = "tma_w8r2c512s3";
+    else want = "tma_w16r1c512s3";
+    for (int v = 0; v < cgb_gemv_variant_count(); ++v)
+        if (std::strcmp(cgb_gemv_variant_name(v), want) == 0) return v;
+    return 0;
+}
+
+void CGSolver::solve(double *x, int NUM_THREADS, int BLOCK_WIDTH, bool T)
+{
+    const int v = gemv_variant_for(NUM_THREADS, BLOCK_WIDTH);
+    for (cgb_ctx *c : m_ctx) {
+        cgb_set_option(c, "gemv_variant", v);
+        cgb_set_option(c, "num_threads", NUM_THREADS);
+        cgb_set_option(c, "block_width", BLOCK_WIDTH);
+        cgb_set_option(c, "transposed", T ? 1 : 0);
+    }
+    std::memset(x, 0, sizeof(double) * (size_t)m_n); // fill<<<>>>(m_n, x, 0.0), cg.cu:217
+    run_solve(x, m_n);                                // for (; k < m_n; ++k), cg.cu:236
+}

@@ -5,7 +5,9 @@ The reference ships no tests or golden vectors, so the pin
 outputs of its own unmodified sources (/root/reference/code/MPI/*.cc, compiled by
 oracle/Makefile into oracle/_ref/ against the stand-in mpi.h/cblas.h) with a real
 OpenBLAS 0.3.15 behind cblas_* ("openblas") and with plain left-to-right loops ("naive").
-Run from the repo root:   python tests/golden/make_golden.py
+Run from the repo root:   python tests/golden/make_golden.py [--full]
+(--full adds BASELINE.json's full-size configs: N=20000 to convergence and N=40000 x 200
+iterations, OpenBLAS provider only; ~2 minutes and 13 GB of host memory.)
 Needs /root/reference (to build oracle/_ref); the produced fixtures are committed so the
 tests never need it.
 
@@ -65,6 +67,13 @@ def main():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
     gen = os.path.join(REF, "cgsolver_ref")
     mtx = os.path.join(REF, "cgsolver_ref_mtx")
+    if "--full" in sys.argv:
+        for n, max_iter in [(20000, None), (40000, 200)]:
+            tail = [] if max_iter is None else [str(max_iter)]
+            runs = {"openblas": run_ref([gen, str(n)], "openblas", tail)}
+            name = f"full_n{n}" + ("" if max_iter is None else f"_it{max_iter}")
+            save(name, dict(n=n, max_iter=n if max_iter is None else max_iter, kind="generate_lap2d"), runs)
+        return
     for n, max_iter in [(1024, None), (2048, None), (4096, None), (1448, 200), (1000, 50)]:
         tail = [] if max_iter is None else [str(max_iter)]
         runs = {blas: run_ref([gen, str(n)], blas, tail) for blas in ("openblas", "naive")}
