@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json: CG iterations/s and mat-vec HBM GB/s
+(fraction of roofline) on generate_lap2d_matrix systems, 1/2/4/8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # N = 1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W          # N > 1, one rank per GPU
+    python bench.py --impl reference ...                                # the reference's CPU path
+
+Workload (config.workload): BASELINE.json configs[2] -- generate_lap2d_matrix N = 40000, dense
+fp64, fixed 200 CG iterations, A row-sharded over the N GPUs by the reference's
+partition_matrix rule (strong scaling: the total work does not grow with N).  `--workload weak`
+runs configs[3] instead (N = 20000 * sqrt(G), 3.2 GB of A per GPU).
+
+A "step" is one pass of the hot path over that system: 200 iterations of CGSolver::solve's loop
+(code/MPI/cg.cc:96-137) = 200 x (mat-vec + gather + fused x/r update + fused p update).
+  value : iterations/s over K steps with everything resident in HBM (cgb_solve_begin outside,
+          cgb_iterate inside the timed region; device time from CUDA events on the solver's
+          stream, max over ranks).
+  e2e   : iterations/s through the call a user of the reference makes -- CGSolver::solve, i.e.
+          cgb_set_rhs + cgb_solve + cgb_residual_check (the DEBUG block the reference keeps in
+          its timed region, cg_main.cc:53-55) -- with x0 / b / x in pinned HOST buffers, the
+          host<->device copies inside the timed region (wall clock, max over ranks).
+  roofline : the mat-vec kernel; algorithmic bytes per launch = 8 * rows_g * N (A read once),
+          duration = average of per-launch CUDA-event pairs inside a real iteration loop.
+  cpu_baseline : the UNMODIFIED reference MPI solver (oracle/_ref/cgsolver_ref, built from
+          /root/reference by oracle/Makefile) on this box's host cores, OpenBLAS threads = all
+          cores, on a bounded sample (fewer iterations of the same N).
+
+The product path is libcgb200.so through its C ABI only.  oracle/ is executed solely for the
+cpu_baseline leg and for --impl reference.
+"""
+import argparse
+import importlib
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "cg_iterations_per_second"
+UNIT = "iterations/s"
+ITERS_PER_STEP = 200          # configs[2] / configs[3]: fixed 200 iterations
+NOMINAL_HBM_GBS = 8000.0      # north_star's denominator ("B200 peak ~8 TB/s")
+FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md, if MEASURED_PEAKS.json is absent
+
+
+def workload_n(kind: str, gpus: int) -> int:
+    if kind == "weak":
+        return {1: 20000, 2: 28284, 4: 40000, 8: 56568}.get(gpus, int(20000 * math.sqrt(gpus)))
+    return 40000
+
+
+def base_config(kind: str, n: int, gpus: int) -> dict:
+    return {
+        "workload": ("generate_lap2d_matrix N=%d dense fp64, fixed %d CG iterations per step, "
+                     "b=init_source_term(1/N), x0=0, tol=1e-10" % (n, ITERS_PER_STEP)),
+        "baseline_config": "configs[2]" if kind == "strong" else "configs[3]",
+        "n": n,
+        "iterations_per_step": ITERS_PER_STEP,
+        "matrix_bytes": 8 * n * n,
+        "sharding": "rows/%d (partition_matrix, cg.cc:236-268)" % gpus,
+        "l2": "inputs larger than L2 (A shard %.1f GB per GPU >> 126 MB)" % (8.0 * n * n / gpus / 1e9),
+    }
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, device copy)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------ reference arm
+def ref_binary():
+    return os.path.join(ROOT, "oracle", "_ref", "cgsolver_ref")
+
+
+def run_reference_cpu(n: int, iters: int, threads: int, skip: int = 0):
+    """Runs the unmodified reference MPI solver (1 rank, OpenBLAS with `threads` threads) for
+    `iters` iterations and returns steady-state numbers from its dgemv timestamps."""
+    exe = ref_binary()
+    if not os.path.exists(exe):
+        raise FileNotFoundError(exe + " (built by oracle/Makefile from /root/reference)")
+    with tempfile.TemporaryDirectory() as td:
+        env = dict(os.environ, CGREF_BLAS="auto", CGREF_GEMV_TIMES=os.path.join(td, "t"),
+                   OPENBLAS_NUM_THREADS=str(threads), OMP_NUM_THREADS=str(threads))
+        t0 = time.time()
+        res = subprocess.run([exe, str(n), os.path.join(td, "results.txt"), str(iters)], env=env,
+                             capture_output=True, text=True)
+        wall = time.time() - t0
+        if res.returncode != 0:
+            raise RuntimeError("reference solver failed: " + res.stderr[-400:])
+        stamps = np.fromfile(os.path.join(td, "t"), dtype=np.float64)
+        row = open(os.path.join(td, "results.txt")).read().strip()
+    # stamps: [init dgemv, loop dgemv x executed, DEBUG dgemv, exit]
+    executed = len(stamps) - 3
+    assert executed >= 1, (len(stamps), res.stdout)
+    lo = 1 + min(skip, executed - 1)
+    timed = executed - (lo - 1)
+    loop_s = float(stamps[1 + executed] - stamps[lo])
+    blas = [ln for ln in res.stderr.splitlines() if ln.startswith("[cgref]")]
+    return dict(iters=executed, timed_iters=timed, loop_seconds=loop_s, it_per_s=timed / loop_s,
+                solve_seconds=float(row.split(",")[2]), wall_seconds=wall,
+                blas=blas[0] if blas else "?", debug_line=res.stdout.strip())
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = workload_n(args.workload, args.gpus)
+    cores = os.cpu_count() or 1
+    # bounded sample: a few iterations per step so that W + K steps end within minutes
+    per_step = max(1, min(5, 60 // max(1, args.steps + args.warmup)))
+    total = per_step * (args.steps + args.warmup)
+    try:
+        r = run_reference_cpu(n, total, cores, skip=per_step * args.warmup)
+    except Exception as e:  # the oracle always exists in a built tree; say why if it does not
+        print(json.dumps({"impl": "reference", "unavailable": str(e)[:200]}))
+        return 0
+    sample = ("unmodified reference code/MPI solver, 1 rank, %s; N=%d; %d iterations per step "
+              "(of %d), %d warm-up + %d timed steps in one process; steady-state loop time from "
+              "dgemv timestamps" % (r["blas"], n, per_step, ITERS_PER_STEP, args.warmup, args.steps))
+    value = r["it_per_s"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * r["loop_seconds"] / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "strong" else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (generate_lap2d_matrix, init_source_term)",
+        "config": base_config(args.workload, n, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gemv_gbs": 8.0 * n * n * value / 1e9,
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.path = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
+        self.proc = None
+        try:
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(device), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.out,
+                stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.close()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
+                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ our arm
+def pinned(n):
+    import torch
+    return torch.zeros(n, dtype=torch.float64).pin_memory().numpy()
+
+
+def product_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus %d must be launched with torch.distributed.run "
+                     "--nproc-per-node %d (one rank per GPU)" % (args.gpus, args.gpus))
+        sys.exit("WORLD_SIZE (%d) != --gpus (%d)" % (world, args.gpus))
+    import torch
+    cgb = importlib.import_module("conjugate-gradient_b200")   # fails loudly without the .so
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; the product has no CPU fallback "
+                 "(use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v: float) -> float:
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v: float) -> float:
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n = workload_n(args.workload, world) if args.n is None else args.n
+    ctx = cgb.Context(n, rank, world, local)
+    if world > 1:
+        box = [cgb.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0])
+    if args.variant is not None:
+        ctx.set_option("gemv_variant", args.variant)
+    for key in ("graph", "graph_unroll", "poll_every", "exchange"):
+        v = getattr(args, key)
+        if v is not None:
+            ctx.set_option(key, v)
+    lay = ctx.layout()
+    ctx.generate_lap2d()                          # device-side generate_lap2d_matrix
+    # init_source_term (cg.cc:218-234) on the host, bit-identical to the reference's libm loop
+    b_host = pinned(n)
+    cgb.init_source_term(n, 1.0 / n, out=b_host)
+    x_host = pinned(n)
+    ctx.set_rhs(b_host)
+    iters = ITERS_PER_STEP if args.iters is None else args.iters
+
+    # ---- value: device-resident steps
+    def step():
+        ctx.solve_begin(None, iters, 1e-10, False)   # x0 = 0 set on the device; not timed
+        ms = ctx.iterate(iters)
+        info = ctx.solve_end(None, None)
+        return ms, info
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    l0 = ctx.launch_count()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    info = None
+    for _ in range(args.steps):
+        ms, info = step()
+        dev_ms += ms
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = allmax(dev_ms)
+    launches_all = int(allsum(float(launches)))
+    done_iters = int(info.iterations)
+    value = args.steps * done_iters / (dev_ms * 1e-3)
+    ms_per_step = dev_ms / args.steps
+    sqrt_rsold = math.sqrt(info.rsold)
+
+    # ---- roofline of the mat-vec: per-launch events inside a real loop, then the kernel alone
+    ctx.set_option("profile", 1)
+    ctx.solve_begin(None, iters, 1e-10, False)
+    ctx.iterate(iters)
+    ctx.solve_end(None, None)
+    gemv_ms, gemv_launches = ctx.last_gemv_timing()
+    ctx.set_option("profile", 0)
+    gemv_ms = allmax(gemv_ms)
+    alone_ms = allmax(ctx.bench_gemv(-1, 20))
+    read_ms = allmax(ctx.bench_read(20))
+    rows_max = max(cgb.partition(n, world)[1])
+    gemv_bytes = 8.0 * rows_max * n               # slowest rank's shard, A read exactly once
+    peak, peak_src = measured_peak()
+    achieved = gemv_bytes / (gemv_ms * 1e-3) / 1e9
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "gemv_traffic.json")
+    if os.path.exists(tr_path):
+        try:
+            tr = json.load(open(tr_path))
+            key = "n%d_rows%d" % (n, rows_max)
+            traffic = tr.get(key, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "kernel": "gemv_tma_kernel (%s)" % cgb.gemv_variants()[ctx.get_option("gemv_variant")],
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": gemv_bytes, "launch_ms": gemv_ms,
+        "launches_timed": int(gemv_launches),
+        "frac_of_nominal_8TBs": achieved / NOMINAL_HBM_GBS,
+        "kernel_alone_gbs": gemv_bytes / (alone_ms * 1e-3) / 1e9,
+        "read_stream_gbs": gemv_bytes / (read_ms * 1e-3) / 1e9,
+        "full_iteration_gbs_per_gpu": 8.0 * n * n / world * value / 1e9,
+        "full_iteration_frac_of_nominal": 8.0 * n * n / world * value / 1e9 / NOMINAL_HBM_GBS,
+    }
+
+    # ---- e2e: the reference-facing solve with host buffers
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        x_host[:] = 0.0
+        ctx.set_rhs(b_host)                                   # H2D 8N
+        inf, _ = ctx.solve(x_host, max_iter=iters, tol=1e-10)  # H2D 8N (x0), D2H 8N (x)
+        nx, rr = ctx.residual_check()                         # DEBUG block, D2H 2 doubles
+        return inf, nx, rr
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        inf, nx, rr = e2e_step()
+    barrier()
+    e2e_s = allmax(time.perf_counter() - t0)
+    e2e_value = e2e_steps * int(inf.iterations) / e2e_s
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 16 * n,
+           "d2h_bytes_per_step": 8 * n + 16 + 48, "steps": e2e_steps,
+           "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "call": "cgb_set_rhs + cgb_solve + cgb_residual_check (= CGSolver::solve incl. DEBUG block), pinned host x0/b/x",
+           "norm_x": nx, "rel_resid": rr}
+
+    # ---- sanity against the golden output of the unmodified reference (same N, 200 iterations)
+    check = None
+    gpath = os.path.join(ROOT, "tests", "golden", "full_n40000_it200.npz")
+    if n == 40000 and iters == 200 and os.path.exists(gpath):
+        g = np.load(gpath)
+        ref_print = float(g["openblas_resid_print"])
+        check = {"sqrt_rsold": sqrt_rsold, "reference_printed": ref_print,
+                 "rel_err": abs(sqrt_rsold - ref_print) / ref_print,
+                 "x_rel_err": float(np.linalg.norm(x_host - g["openblas_x"]) / np.linalg.norm(g["openblas_x"]))}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample_iters = args.cpu_iters
+        try:
+            r = run_reference_cpu(n, sample_iters, cores)
+            cpu_baseline = {
+                "value": r["it_per_s"], "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": ("unmodified reference code/MPI solver (oracle/_ref/cgsolver_ref), 1 rank, %s, "
+                           "N=%d, %d of the %d iterations; steady-state loop time from dgemv timestamps "
+                           "(%.2f s loop, %.1f s process incl. its -O0 matrix generation)"
+                           % (r["blas"], n, r["iters"], iters, r["loop_seconds"], r["wall_seconds"])),
+                "gemv_gbs": 8.0 * n * n * r["it_per_s"] / 1e9,
+            }
+        except Exception as e:
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference",
+                            "sample": "unavailable: " + str(e)[:200]}
+
+    if dist is not None:
+        dist.barrier()
+    ctx.close()
+    if rank == 0:
+        cfg = base_config(args.workload, n, world)
+        cfg.update({"gemv_variant": roofline["kernel"], "nblk": lay.nblk,
+                    "graph": ctx_opts(args), "parallelism": "rows%d" % world})
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "strong" else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (generate_lap2d_matrix, init_source_term)",
+            "config": cfg, "ms_per_iteration": ms_per_step / done_iters,
+            "gemv_gbs_per_gpu": achieved, "wall_s_timed_region": wall_s,
+            "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline,
+            "gpu_launches": launches_all, "clocks": clocks, "check": check,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def ctx_opts(args):
+    return {k: getattr(args, k) for k in ("graph", "graph_unroll", "poll_every", "exchange")
+            if getattr(args, k) is not None} or "defaults"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=["strong", "weak"], default="strong")
+    ap.add_argument("--n", type=int, default=None, help="override N (not a bench line)")
+    ap.add_argument("--iters", type=int, default=None, help="override iterations per step")
+    ap.add_argument("--variant", type=int, default=None)
+    ap.add_argument("--graph", type=int, default=None)
+    ap.add_argument("--graph-unroll", dest="graph_unroll", type=int, default=None)
+    ap.add_argument("--poll-every", dest="poll_every", type=int, default=None)
+    ap.add_argument("--exchange", type=int, default=None)
+    ap.add_argument("--cpu-iters", dest="cpu_iters", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("bench.py: note: fewer than 3 warm-up steps requested", file=sys.stderr)
+    if args.impl == "reference":
+        return reference_arm(args)
+    return product_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -9,7 +9,7 @@ The directory name contains a hyphen, so import it with
     importlib.import_module("conjugate-gradient_b200")
 """
 from ._capi import (CgbError, Context, Layout, SolveInfo, SIGNATURES, LIB_PATH, UNIQUE_ID_BYTES,
-                    device_count, gemv_variants, load, partition, unique_id)
+                    device_count, gemv_variants, init_source_term, load, partition, unique_id)
 
 __all__ = ["CgbError", "Context", "Layout", "SolveInfo", "SIGNATURES", "LIB_PATH",
-           "UNIQUE_ID_BYTES", "device_count", "gemv_variants", "load", "partition", "unique_id"]
+           "UNIQUE_ID_BYTES", "device_count", "gemv_variants", "init_source_term", "load", "partition", "unique_id"]

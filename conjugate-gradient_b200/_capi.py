@@ -51,6 +51,7 @@ SIGNATURES = [
     ("cgb_set_matrix_rows", C.c_int, [_CTX, _dp, C.c_int64, C.c_int64, C.c_int64]),
     ("cgb_set_matrix_coo", C.c_int, [_CTX, C.c_int64, _i32p, _i32p, _dp, C.c_int]),
     ("cgb_get_matrix_rows", C.c_int, [_CTX, _dp, C.c_int64, C.c_int64, C.c_int64]),
+    ("cgb_init_source_term", C.c_int, [C.c_int64, C.c_double, _dp]),
     ("cgb_set_rhs", C.c_int, [_CTX, _dp]),
     ("cgb_set_option", C.c_int, [_CTX, C.c_char_p, C.c_int64]),
     ("cgb_get_option", C.c_int, [_CTX, C.c_char_p, _i64p]),
@@ -113,6 +114,13 @@ def partition(n: int, psize: int):
     c = (C.c_int64 * psize)()
     _check(load().cgb_partition(n, psize, s, c))
     return list(s), list(c)
+
+
+def init_source_term(n: int, h: float | None = None, out: np.ndarray | None = None) -> np.ndarray:
+    """b of CGSolver::init_source_term (host libm loop inside the library, as in the reference)."""
+    b = np.empty(n, dtype=np.float64) if out is None else out
+    _check(load().cgb_init_source_term(n, (1.0 / n) if h is None else h, _p(b)))
+    return b
 
 
 def unique_id() -> bytes:

@@ -536,6 +536,16 @@ extern "C" int cgb_get_matrix_rows(cgb_ctx *c, double *rows_host, int64_t first_
     return CGB_OK;
 }
 
+extern "C" int cgb_init_source_term(int64_t n, double h, double *b_host)
+{
+    if (n < 0 || (n > 0 && !b_host)) return fail(CGB_ERR_INVALID, "bad source-term arguments");
+    for (int64_t i = 0; i < n; ++i) { // cg.cc:222-233
+        const double s = std::sin(10. * M_PI * i * h);
+        b_host[i] = -2. * i * M_PI * M_PI * s * s;
+    }
+    return CGB_OK;
+}
+
 extern "C" int cgb_set_rhs(cgb_ctx *c, const double *b_host)
 {
     int rc = use_device(c);

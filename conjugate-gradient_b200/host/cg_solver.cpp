@@ -122,9 +122,8 @@ void CGSolver::set_max_iter(int maxIter) { m_maxIter = maxIter; }
 void CGSolver::init_source_term(double h)
 {
     m_b.resize(m_n);
-    for (int i = 0; i < m_n; i++) {
-        m_b[i] = -2. * i * M_PI * M_PI * std::sin(10. * M_PI * i * h) * std::sin(10. * M_PI * i * h);
-    }
+    const int rc = cgb_init_source_term(m_n, h, m_b.data());
+    if (rc) raise("cgb_init_source_term", rc);
     m_rhs_uploaded = false;
 }
 

@@ -84,6 +84,12 @@ int cgb_set_matrix_coo(cgb_ctx *ctx, int64_t nz, const int32_t *irn, const int32
 int cgb_get_matrix_rows(cgb_ctx *ctx, double *rows_host, int64_t first_row, int64_t nrows,
                         int64_t ld_host);
 
+/* CGSolver::init_source_term (code/MPI/cg.cc:218-234, code/CUDA/cg.cu:324-340):
+ * b_i = -2 i pi^2 sin(10 pi i h)^2 into a caller-owned HOST buffer of n doubles.  Like the
+ * reference this is a host loop over libm sin (the values feed cgb_set_rhs); it is the one
+ * entry point that needs no GPU. */
+int cgb_init_source_term(int64_t n, double h, double *b_host);
+
 /* Right-hand side m_b (filled on the host by init_source_term, cg.cc:218-234, so that libm
  * sin is shared with the reference), full length n. */
 int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
