@@ -119,7 +119,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n = workload_n(args.workload, args.gpus)
+    n = workload_n(args.workload, args.gpus) if args.n is None else args.n
     cores = os.cpu_count() or 1
     # bounded sample: a few iterations per step so that W + K steps end within minutes
     per_step = max(1, min(5, 60 // max(1, args.steps + args.warmup)))
@@ -247,9 +247,10 @@ def product_arm(args):
     n = workload_n(args.workload, world) if args.n is None else args.n
     ctx = cgb.Context(n, rank, world, local)
     if world > 1:
-        box = [cgb.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        ctx.comm_init(box[0])
+        # wiring (replaces MPI_Init): NCCL id for the ncclAllGather baseline, exchange blobs
+        # (CUDA IPC) for the fused peer-store exchange; --exchange 0/1 picks one (default fused)
+        wiring = importlib.import_module("conjugate-gradient_b200.wiring")
+        wiring.wire(ctx, rank, world, dist, cgb.unique_id)
     if args.variant is not None:
         ctx.set_option("gemv_variant", args.variant)
     for key in ("graph", "graph_unroll", "poll_every", "exchange"):
@@ -257,6 +258,8 @@ def product_arm(args):
         if v is not None:
             ctx.set_option(key, v)
     lay = ctx.layout()
+    exchange_name = ("none (1 GPU)" if world == 1 else
+                     ["ncclAllGather", "fused peer stores + flags in the mat-vec kernel"][ctx.get_option("exchange")])
     ctx.generate_lap2d()                          # device-side generate_lap2d_matrix
     # init_source_term (cg.cc:218-234) on the host, bit-identical to the reference's libm loop
     b_host = pinned(n)
@@ -388,7 +391,8 @@ def product_arm(args):
     if rank == 0:
         cfg = base_config(args.workload, n, world)
         cfg.update({"gemv_variant": roofline["kernel"], "nblk": lay.nblk,
-                    "graph": ctx_opts(args), "parallelism": "rows%d" % world})
+                    "graph": ctx_opts(args), "parallelism": "rows%d" % world,
+                    "exchange": exchange_name})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -417,7 +421,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=["strong", "weak"], default="strong")
-    ap.add_argument("--n", type=int, default=None, help="override N (not a bench line)")
+    ap.add_argument("--size", dest="n", type=int, default=None, help="override N (not a bench line)")
     ap.add_argument("--iters", type=int, default=None, help="override iterations per step")
     ap.add_argument("--variant", type=int, default=None)
     ap.add_argument("--graph", type=int, default=None)

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcgb200.so")
 
 UNIQUE_ID_BYTES = 128
+EXCHANGE_BLOB_BYTES = 128
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)
 _i32p = C.POINTER(C.c_int32)
@@ -47,6 +48,8 @@ SIGNATURES = [
     ("cgb_destroy", C.c_int, [_CTX]),
     ("cgb_comm_unique_id", C.c_int, [C.c_void_p]),
     ("cgb_comm_init", C.c_int, [_CTX, C.c_void_p]),
+    ("cgb_exchange_export", C.c_int, [_CTX, C.c_void_p]),
+    ("cgb_exchange_import", C.c_int, [_CTX, C.c_void_p]),
     ("cgb_generate_lap2d", C.c_int, [_CTX]),
     ("cgb_set_matrix_rows", C.c_int, [_CTX, _dp, C.c_int64, C.c_int64, C.c_int64]),
     ("cgb_set_matrix_coo", C.c_int, [_CTX, C.c_int64, _i32p, _i32p, _dp, C.c_int]),
@@ -164,6 +167,18 @@ class Context:
     def comm_init(self, uid: bytes):
         buf = C.create_string_buffer(uid, UNIQUE_ID_BYTES)
         _check(self._lib.cgb_comm_init(self._h, buf))
+
+    def exchange_export(self) -> bytes:
+        buf = C.create_string_buffer(EXCHANGE_BLOB_BYTES)
+        _check(self._lib.cgb_exchange_export(self._h, buf))
+        return buf.raw
+
+    def exchange_import(self, blobs):
+        """blobs: one exchange_export() result per rank, in rank order."""
+        raw = b"".join(blobs)
+        assert len(raw) == EXCHANGE_BLOB_BYTES * len(blobs)
+        buf = C.create_string_buffer(raw, len(raw))
+        _check(self._lib.cgb_exchange_import(self._h, buf))
 
     def layout(self) -> Layout:
         lay = Layout()

@@ -4,10 +4,15 @@
 // Multi-GPU design (replaces MPI_Allgatherv + 2 x MPI_Allreduce per iteration,
 // code/MPI/cg.cc:105-136): A is row-sharded by the reference's partition rule; the O(N) vectors
 // x, r, p are REPLICATED and updated redundantly by every rank, so the only exchange per
-// iteration is ONE all-gather of [Ap rows | p'Ap block partials] after the mat-vec
-// (ncclAllGather, in place).  The scalars (alpha, beta, r'r, the stop test) are then computed
-// by every rank from identical data in an identical order: bitwise equal on all ranks without
-// any all-reduce.
+// iteration is ONE all-gather of [Ap rows | p'Ap block partials] after the mat-vec.  The
+// scalars (alpha, beta, r'r, the stop test) are then computed by every rank from identical
+// data in an identical order: bitwise equal on all ranks without any all-reduce.
+// Two implementations of that exchange (option "exchange"):
+//   1 (default once cgb_exchange_import was called)  FUSED: the mat-vec kernel stores every
+//     finished row straight into all peers' gather buffers over NVLink (peer-mapped memory,
+//     cudaIpc across processes) and its last CTA raises a flag on every rank; the x/r update
+//     kernel spins on its local flags.  No collective kernel, nothing between the two launches.
+//   0  ncclAllGather (in place) between the two kernels -- the baseline to beat.
 #include "../../include/cgb200.h"
 #include "cgb_kernels.h"
 
@@ -18,6 +23,7 @@
 #include <dlfcn.h>
 #include <new>
 #include <string>
+#include <unistd.h>
 #include <unordered_map>
 #include <vector>
 
@@ -106,6 +112,15 @@ struct cgb_ctx {
 
     double *A = nullptr, *p = nullptr, *r = nullptr, *x = nullptr, *b = nullptr;
     double *apx = nullptr, *rrpart = nullptr, *scratch = nullptr, *hist = nullptr, *sink = nullptr;
+    // gather buffers: apx = [2][world][slot_cap] doubles followed by the Ctl words
+    long long bufstride = 0;
+    size_t apx_bytes = 0;
+    Ctl *ctl = nullptr;
+    double *peer_base[kMaxWorld] = {};
+    Ctl *peer_ctl[kMaxWorld] = {};
+    void *ipc_opened[kMaxWorld] = {};
+    bool p2p_ready = false;
+    int opt_exchange = 0; // 0 = ncclAllGather, 1 = fused peer stores
     long long hist_cap = 0;
     State *st = nullptr;
     int *h_done = nullptr, *d_hdone = nullptr; // mapped pinned flag
@@ -143,6 +158,9 @@ Gather make_gather(const cgb_ctx *c)
     g.maxrows = c->maxrows;
     g.world = c->world;
     g.nblk = c->nblk;
+    g.bufstride = c->bufstride;
+    g.ctl = c->ctl;
+    g.p2p = (c->world > 1 && c->opt_exchange == 1) ? 1 : 0;
     return g;
 }
 
@@ -152,8 +170,17 @@ GemvArgs make_gemv_args(const cgb_ctx *c, const double *v, int advance)
     memset(&a, 0, sizeof a);
     a.A = c->A;
     a.v = v;
-    a.out = c->apx + (long long)c->rank * c->slot;
-    a.npeers = 0;
+    a.base = c->apx;
+    a.ctl = c->ctl;
+    a.bufstride = c->bufstride;
+    a.slot_off = (long long)c->rank * c->slot;
+    a.rank = c->rank;
+    a.world = c->world;
+    a.p2p = (c->world > 1 && c->opt_exchange == 1) ? 1 : 0;
+    for (int g = 0; g < kMaxWorld; ++g) {
+        a.peer_base[g] = c->peer_base[g];
+        a.peer_ctl[g] = c->peer_ctl[g];
+    }
     a.ld = c->ld;
     a.rows = c->rows;
     a.row0 = c->row0;
@@ -212,7 +239,8 @@ int launch_matvec(cgb_ctx *c, const double *v, int advance, int variant)
 int launch_gather(cgb_ctx *c)
 {
     if (c->world == 1) return CGB_OK;
-    if (!c->comm) return fail(CGB_ERR_STATE, "world > 1 but cgb_comm_init was not called");
+    if (c->opt_exchange == 1) return CGB_OK; // fused into the mat-vec kernel (peer stores + flags)
+    if (!c->comm) return fail(CGB_ERR_STATE, "world > 1 but neither cgb_comm_init nor cgb_exchange_import was called");
     NK(g_nccl.AllGather(c->apx + (long long)c->rank * c->slot, c->apx, (size_t)c->slot, kNcclDouble,
                         c->comm, c->stream));
     return CGB_OK;
@@ -248,6 +276,21 @@ int build_graph(cgb_ctx *c)
     c->graph = g;
     CK(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
     c->graph_tol = c->tol; // tol and the history pointer are baked into the captured arguments
+    return CGB_OK;
+}
+
+bool exchange_configured(const cgb_ctx *c)
+{
+    return c->world == 1 || (c->opt_exchange == 1 ? c->p2p_ready : c->comm != nullptr);
+}
+
+// the gather buffer the consumers currently read (hooks that memcpy out of it)
+int current_rbuf(cgb_ctx *c, const double **base)
+{
+    Ctl h;
+    CK(cudaMemcpyAsync(&h, c->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *base = c->apx + (long long)h.rbuf * c->bufstride;
     return CGB_OK;
 }
 
@@ -357,7 +400,12 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
     CKB(cudaMalloc(&c->r, vec_bytes));
     CKB(cudaMalloc(&c->x, vec_bytes));
     CKB(cudaMalloc(&c->b, vec_bytes));
-    CKB(cudaMalloc(&c->apx, (size_t)c->world * c->slot_cap * sizeof(double)));
+    c->bufstride = (long long)c->world * c->slot_cap;
+    c->apx_bytes = (size_t)2 * c->bufstride * sizeof(double) + sizeof(Ctl);
+    CKB(cudaMalloc(&c->apx, c->apx_bytes));
+    c->ctl = reinterpret_cast<Ctl *>(c->apx + 2 * c->bufstride);
+    c->peer_base[rank] = c->apx;
+    c->peer_ctl[rank] = c->ctl;
     CKB(cudaMalloc(&c->rrpart, (size_t)c->nchunks * sizeof(double)));
     CKB(cudaMalloc(&c->scratch, (size_t)(3 * c->nchunks + 8) * sizeof(double)));
     CKB(cudaMalloc(&c->sink, 64));
@@ -371,7 +419,7 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
     CKB(cudaMemsetAsync(c->r, 0, vec_bytes, c->stream));
     CKB(cudaMemsetAsync(c->x, 0, vec_bytes, c->stream));
     CKB(cudaMemsetAsync(c->b, 0, vec_bytes, c->stream));
-    CKB(cudaMemsetAsync(c->apx, 0, (size_t)c->world * c->slot_cap * sizeof(double), c->stream));
+    CKB(cudaMemsetAsync(c->apx, 0, c->apx_bytes, c->stream));
     CKB(cudaMemsetAsync(c->rrpart, 0, (size_t)c->nchunks * sizeof(double), c->stream));
     CKB(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
     CKB(cudaStreamSynchronize(c->stream));
@@ -388,6 +436,8 @@ extern "C" int cgb_destroy(cgb_ctx *c)
     drop_graph(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    for (void *p : c->ipc_opened)
+        if (p) cudaIpcCloseMemHandle(p);
     double *bufs[] = {c->A, c->p, c->r, c->x, c->b, c->apx, c->rrpart, c->scratch, c->hist, c->sink};
     for (double *p : bufs)
         if (p) cudaFree(p);
@@ -425,6 +475,78 @@ extern "C" int cgb_comm_init(cgb_ctx *c, const void *id_in)
     ncclUniqueId id;
     memcpy(&id, id_in, sizeof id);
     NK(g_nccl.CommInitRank(&c->comm, c->world, id, c->rank));
+    return CGB_OK;
+}
+
+// ---- fused exchange wiring -------------------------------------------------------------
+namespace {
+struct XchBlob {
+    uint64_t magic;
+    int32_t pid, device, rank, world;
+    uint64_t ptr, bytes;
+    cudaIpcMemHandle_t handle;
+};
+static_assert(sizeof(XchBlob) <= CGB_EXCHANGE_BLOB_BYTES, "exchange blob too large");
+constexpr uint64_t kXchMagic = 0x6367623230307832ULL;
+} // namespace
+
+extern "C" int cgb_exchange_export(cgb_ctx *c, void *blob_out)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (!blob_out) return fail(CGB_ERR_INVALID, "null blob");
+    XchBlob b;
+    memset(&b, 0, sizeof b);
+    b.magic = kXchMagic;
+    b.pid = (int32_t)getpid();
+    b.device = c->device;
+    b.rank = c->rank;
+    b.world = c->world;
+    b.ptr = (uint64_t)(uintptr_t)c->apx;
+    b.bytes = c->apx_bytes;
+    CK(cudaIpcGetMemHandle(&b.handle, c->apx));
+    memset(blob_out, 0, CGB_EXCHANGE_BLOB_BYTES);
+    memcpy(blob_out, &b, sizeof b);
+    return CGB_OK;
+}
+
+extern "C" int cgb_exchange_import(cgb_ctx *c, const void *blobs)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (c->world == 1) return CGB_OK;
+    if (!blobs) return fail(CGB_ERR_INVALID, "null blobs");
+    if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
+    if (c->p2p_ready) return fail(CGB_ERR_STATE, "exchange already imported");
+    const char *base = static_cast<const char *>(blobs);
+    for (int g = 0; g < c->world; ++g) {
+        XchBlob b;
+        memcpy(&b, base + (size_t)g * CGB_EXCHANGE_BLOB_BYTES, sizeof b);
+        if (b.magic != kXchMagic || b.rank != g || b.world != c->world || b.bytes != c->apx_bytes)
+            return fail(CGB_ERR_INVALID, "exchange blob %d does not match this context "
+                        "(rank %d world %d bytes %llu)", g, b.rank, b.world, (unsigned long long)b.bytes);
+        if (g == c->rank) continue;
+        void *ptr = nullptr;
+        if (b.pid == (int32_t)getpid()) { // same process (threads): plain peer access
+            if (b.device != c->device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, c->device, b.device));
+                if (!can) return fail(CGB_ERR_CUDA, "device %d cannot access peer %d", c->device, b.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else CK(e);
+            }
+            ptr = (void *)(uintptr_t)b.ptr;
+        } else {
+            CK(cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened[g] = ptr;
+        }
+        c->peer_base[g] = static_cast<double *>(ptr);
+        c->peer_ctl[g] = reinterpret_cast<Ctl *>(c->peer_base[g] + 2 * c->bufstride);
+    }
+    c->p2p_ready = true;
+    c->opt_exchange = 1;
+    drop_graph(c);
     return CGB_OK;
 }
 
@@ -580,6 +702,14 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
         if (value < 1 || value > 64) return fail(CGB_ERR_INVALID, "graph_unroll must be in [1, 64]");
         c->graph_unroll = (int)value;
         drop_graph(c);
+    } else if (k == "exchange") {
+        if (value != 0 && value != 1) return fail(CGB_ERR_INVALID, "exchange must be 0 (nccl) or 1 (fused p2p)");
+        if (c->world > 1 && value == 1 && !c->p2p_ready)
+            return fail(CGB_ERR_STATE, "exchange = 1 needs cgb_exchange_import first");
+        if (c->world > 1 && value == 0 && !c->comm)
+            return fail(CGB_ERR_STATE, "exchange = 0 needs cgb_comm_init first");
+        c->opt_exchange = (int)value;
+        drop_graph(c);
     } else if (k == "num_threads") {
         c->opt_num_threads = (int)value;
     } else if (k == "block_width") {
@@ -601,6 +731,7 @@ extern "C" int cgb_get_option(cgb_ctx *c, const char *key, int64_t *value)
     else if (k == "profile") *value = c->opt_profile;
     else if (k == "poll_every") *value = c->poll_every;
     else if (k == "graph_unroll") *value = c->graph_unroll;
+    else if (k == "exchange") *value = c->opt_exchange;
     else if (k == "num_threads") *value = c->opt_num_threads;
     else if (k == "block_width") *value = c->opt_block_width;
     else if (k == "transposed") *value = c->opt_transposed;
@@ -634,7 +765,8 @@ extern "C" int cgb_solve_begin(cgb_ctx *c, const double *x0_host, int64_t max_it
     if (!c->rhs_set) return fail(CGB_ERR_STATE, "right-hand side not set");
     if (c->in_solve) return fail(CGB_ERR_STATE, "solve already in progress");
     if (max_iter < 0) return fail(CGB_ERR_INVALID, "max_iter < 0");
-    if (c->world > 1 && !c->comm) return fail(CGB_ERR_STATE, "world > 1 but cgb_comm_init was not called");
+    if (!exchange_configured(c))
+        return fail(CGB_ERR_STATE, "world > 1 but neither cgb_comm_init nor cgb_exchange_import was called");
     c->max_iter = max_iter;
     c->tol = tol;
     if (c->graph_exec && c->graph_tol != tol) drop_graph(c);
@@ -822,16 +954,24 @@ extern "C" int cgb_gemv(cgb_ctx *c, const double *v_host, double *y_host, double
     if (!v_host) return fail(CGB_ERR_INVALID, "null v");
     CK(cudaMemsetAsync(&c->st->done, 0, sizeof(int), c->stream));
     CK(cudaMemcpyAsync(c->p, v_host, (size_t)c->n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (!exchange_configured(c)) return fail(CGB_ERR_STATE, "world > 1 but no exchange is configured");
     if ((rc = launch_matvec(c, c->p, 0, c->variant))) return rc;
     if ((rc = launch_gather(c))) return rc;
-    const double *mine = c->apx + (long long)c->rank * c->slot;
+    const Gather gth = make_gather(c);
+    if (gth.p2p) {
+        CK(launch_exchange_wait(gth, c->stream));
+        c->kernel_launches += 1;
+    }
+    const double *rb = nullptr;
+    if ((rc = current_rbuf(c, &rb))) return rc;
+    const double *mine = rb + (long long)c->rank * c->slot;
     if (y_host) CK(cudaMemcpyAsync(y_host, mine, (size_t)c->rows * 8, cudaMemcpyDeviceToHost, c->stream));
     if (block_partials)
         CK(cudaMemcpyAsync(block_partials, mine + c->maxrows, (size_t)c->nblk * 8, cudaMemcpyDeviceToHost,
                            c->stream));
     if (pAp) {
         double *out = c->scratch + 3 * c->nchunks;
-        CK(launch_sum_partials(c->apx, make_gather(c), out, c->stream));
+        CK(launch_sum_partials(c->apx, gth, out, c->stream));
         c->kernel_launches += 1;
         CK(cudaMemcpyAsync(c->h_pin, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }

@@ -24,22 +24,43 @@ struct State {
     int pad;
 };
 
+// Control words of the mat-vec exchange, in device memory next to the gather buffers (and, in
+// P2P mode, written by the peers over NVLink).
+struct Ctl {
+    unsigned long long flags[kMaxWorld]; // flags[g] = number of exchanges rank g has delivered here
+    unsigned long long epoch;            // exchanges this rank has sent
+    unsigned int arrive;                 // CTAs of the running mat-vec that have finished
+    int wbuf;                            // gather buffer the next mat-vec writes   (P2P: alternates)
+    int rbuf;                            // gather buffer the consumers read        (P2P: alternates)
+    int pad;
+};
+
 // Geometry of the gathered mat-vec result: rank g owns slot g of `slot` doubles,
 // [0, rows_g) = its Ap rows, [maxrows, maxrows + nblk) = its p'Ap block partials.
+// Two such buffers (`bufstride` doubles apart) exist; only P2P mode uses the second.
 struct Gather {
     long long n_loc;   // rows of every rank but the last (N / world)
     long long slot;    // doubles per rank slot
     long long maxrows; // rows of the last rank (the largest shard)
+    long long bufstride;
+    const Ctl *ctl;
     int world;
     int nblk;
+    int p2p;           // 1: wait for the peers' flags before reading (fused exchange)
 };
 
 struct GemvArgs {
     const double *A;      // rows x ld shard, zero-padded columns
     const double *v;      // input vector, ld doubles, zero-padded
-    double *out;          // this rank's slot of the gathered result
-    double *peer_out[kMaxWorld]; // P2P mode: the same slot in every peer's buffer (self included)
-    int npeers;           // 0 = local store only
+    double *base;         // local gather buffers (2 x bufstride doubles)
+    double *peer_base[kMaxWorld]; // P2P mode: every rank's gather buffers (self included)
+    Ctl *ctl;
+    Ctl *peer_ctl[kMaxWorld];
+    long long bufstride;
+    long long slot_off;   // rank * slot: where this rank's slot starts inside a buffer
+    int rank;
+    int world;
+    int p2p;              // 1: store rows + partials straight into every peer, then raise flags
     long long ld;
     long long rows;
     long long row0;       // global index of the shard's first row (index into v)
@@ -105,6 +126,48 @@ __device__ __forceinline__ double block_chunk256(double v, double *wsum, int tid
         t = __dadd_rn(t, shfl_xor_f64(t, 1));
     }
     return t;
+}
+
+// ------------------------------------------------------------------ exchange (P2P mode)
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Consumer side of the fused exchange: block until every rank has delivered the mat-vec result
+// this rank has itself just sent (epoch).  Threads 0..world-1 each poll one LOCAL flag; the
+// wait is bounded (a dead peer faults the launch instead of hanging the GPU).  Ends with a
+// block barrier, so it must be called by all threads of the block.
+__device__ __forceinline__ void exchange_wait(const Gather &g, int tid)
+{
+    if (g.p2p) {
+        if (tid < g.world) {
+            const unsigned long long want = g.ctl->epoch;
+            if (ld_acquire_sys_u64(&g.ctl->flags[tid]) < want) {
+                const unsigned long long t0 = globaltimer_ns();
+                while (ld_acquire_sys_u64(&g.ctl->flags[tid]) < want) {
+                    if (globaltimer_ns() - t0 > 20000000000ULL) __trap();
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+// base of the gather buffer the consumers read
+__device__ __forceinline__ const double *gather_rbuf(const double *apx, const Gather &g)
+{
+    return apx + (long long)g.ctl->rbuf * g.bufstride;
 }
 
 __device__ __forceinline__ long long gather_index(const Gather &g, long long i)

@@ -34,9 +34,11 @@ __global__ void __launch_bounds__(kChunk) init_residual_kernel(const VecArgs a)
     __shared__ double wsum[8];
     const int tid = threadIdx.x;
     const long long i = (long long)blockIdx.x * kChunk + tid;
+    exchange_wait(a.g, tid);
+    const double *apx = gather_rbuf(a.apx, a.g);
     double v = 0.0;
     if (i < a.n) {
-        const double ap = a.apx[gather_index(a.g, i)];
+        const double ap = apx[gather_index(a.g, i)];
         const double rr = __fma_rn(-1.0, ap, a.b[i]); // daxpy(-1, Ap, r = b)   cg.cc:82
         a.r[i] = rr;
         a.p[i] = rr;                                  // p = r                  cg.cc:85
@@ -53,10 +55,12 @@ __global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a)
     __shared__ double sh_alpha;
     if (a.st->done) return;
     const int tid = threadIdx.x;
+    exchange_wait(a.g, tid);                 // fused exchange: the peers' rows have landed
+    const double *apx = gather_rbuf(a.apx, a.g);
     const int total = a.g.world * a.g.nblk;
     for (int t = tid; t < total; t += kChunk) {
         const int r = t / a.g.nblk, c = t - r * a.g.nblk;
-        sh_part[t] = a.apx[(long long)r * a.g.slot + a.g.maxrows + c];
+        sh_part[t] = apx[(long long)r * a.g.slot + a.g.maxrows + c];
     }
     __syncthreads();
     if (tid < 32) {
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a)
     if (i < a.n) {
         const double pi = a.p[i];
         a.x[i] = __fma_rn(alpha, pi, a.x[i]);                          // cg.cc:110
-        const double rn = __fma_rn(-alpha, a.apx[gather_index(a.g, i)], a.r[i]); // cg.cc:113
+        const double rn = __fma_rn(-alpha, apx[gather_index(a.g, i)], a.r[i]); // cg.cc:113
         a.r[i] = rn;
         v = __dmul_rn(rn, rn);                                         // cg.cc:116
     }
@@ -135,10 +139,12 @@ __global__ void __launch_bounds__(kChunk) debug_partials_kernel(const VecArgs a,
     __shared__ double wsum[8];
     const int tid = threadIdx.x;
     const long long i = (long long)blockIdx.x * kChunk + tid;
+    exchange_wait(a.g, tid);
+    const double *apx = gather_rbuf(a.apx, a.g);
     double dd = 0.0, bb = 0.0, xx = 0.0;
     if (i < a.n) {
         const double bi = a.b[i], xi = a.x[i];
-        const double d = __fma_rn(-1.0, bi, a.apx[gather_index(a.g, i)]); // cg.cc:146-148
+        const double d = __fma_rn(-1.0, bi, apx[gather_index(a.g, i)]); // cg.cc:146-148
         dd = __dmul_rn(d, d);
         bb = __dmul_rn(bi, bi);
         xx = __dmul_rn(xi, xi);
@@ -185,9 +191,13 @@ __global__ void __launch_bounds__(32) sum_kernel(const double *v, long long n, d
 
 __global__ void __launch_bounds__(32) sum_partials_kernel(const double *apx, const Gather g, double *out)
 {
-    const double s = warp_det_sum_partials(apx, g, threadIdx.x);
+    exchange_wait(g, threadIdx.x);
+    const double s = warp_det_sum_partials(gather_rbuf(apx, g), g, threadIdx.x);
     if (threadIdx.x == 0) out[0] = s;
 }
+
+// hooks that read the gather buffer with a memcpy wait for the exchange with this kernel
+__global__ void __launch_bounds__(32) exchange_wait_kernel(const Gather g) { exchange_wait(g, threadIdx.x); }
 
 // generate_lap2d_matrix (cg.cc:159-188): every element of the shard is written once, two
 // columns per thread (128-bit stores); padding columns [n, ld) are zero.
@@ -283,6 +293,12 @@ cudaError_t launch_dot(const double *a, const double *b, long long n, double *sc
 cudaError_t launch_sum_partials(const double *apx, const Gather &g, double *out, cudaStream_t s)
 {
     sum_partials_kernel<<<1, 32, 0, s>>>(apx, g, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exchange_wait(const Gather &g, cudaStream_t s)
+{
+    exchange_wait_kernel<<<1, 32, 0, s>>>(g);
     return cudaGetLastError();
 }
 

@@ -5,6 +5,7 @@
 #include "matrix_coo.hpp"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <mutex>
@@ -74,13 +75,26 @@ void CGSolver::ensure_contexts(int64_t n)
     }
     m_ctx_n = n;
     if (G > 1) { // replaces MPI_Init / MPI_COMM_WORLD (cg_main.cc:15-20)
-        char id[CGB_UNIQUE_ID_BYTES];
-        int rc = cgb_comm_unique_id(id);
-        if (rc) raise("cgb_comm_unique_id", rc);
-        on_all_ranks([&](int r) {
-            const int rc2 = cgb_comm_init(m_ctx[r], id);
-            if (rc2) raise("cgb_comm_init", rc2);
-        });
+        const char *mode = std::getenv("CGB_EXCHANGE"); // "nccl" selects ncclAllGather
+        if (mode && std::string(mode) == "nccl") {
+            char id[CGB_UNIQUE_ID_BYTES];
+            int rc = cgb_comm_unique_id(id);
+            if (rc) raise("cgb_comm_unique_id", rc);
+            on_all_ranks([&](int r) {
+                const int rc2 = cgb_comm_init(m_ctx[r], id);
+                if (rc2) raise("cgb_comm_init", rc2);
+            });
+        } else { // default: the exchange fused into the mat-vec kernel (peer stores over NVLink)
+            std::vector<char> blobs((size_t)G * CGB_EXCHANGE_BLOB_BYTES);
+            for (int r = 0; r < G; ++r) {
+                const int rc = cgb_exchange_export(m_ctx[r], blobs.data() + (size_t)r * CGB_EXCHANGE_BLOB_BYTES);
+                if (rc) raise("cgb_exchange_export", rc);
+            }
+            for (int r = 0; r < G; ++r) {
+                const int rc = cgb_exchange_import(m_ctx[r], blobs.data());
+                if (rc) raise("cgb_exchange_import", rc);
+            }
+        }
     }
     if (m_variant >= 0)
         for (cgb_ctx *c : m_ctx) {

@@ -63,6 +63,18 @@ int cgb_destroy(cgb_ctx *ctx);
 int cgb_comm_unique_id(void *id_out);
 int cgb_comm_init(cgb_ctx *ctx, const void *id);
 
+/* Fused exchange (the B200-native replacement of MPI_Allgatherv, cg.cc:135-136): the mat-vec
+ * kernel stores its rows directly into every rank's gather buffer over NVLink and raises a
+ * flag; no collective kernel runs.  Every rank exports a blob describing its buffer, the blobs
+ * are shipped to all ranks by any means (world x CGB_EXCHANGE_BLOB_BYTES, rank order) and
+ * imported; ranks may be threads of one process (peer access) or separate processes (CUDA
+ * IPC).  After the import the option "exchange" is 1 (fused); 0 selects ncclAllGather, which
+ * needs cgb_comm_init instead.  Like a collective, every rank must issue the same sequence of
+ * solves / mat-vec hooks. */
+#define CGB_EXCHANGE_BLOB_BYTES 128
+int cgb_exchange_export(cgb_ctx *ctx, void *blob_out);
+int cgb_exchange_import(cgb_ctx *ctx, const void *blobs);
+
 /* ---- inputs -------------------------------------------------------------------------- */
 /* CGSolver::generate_lap2d_matrix (code/MPI/cg.cc:159-188), written straight into this
  * rank's device shard (values exactly 0, -1, 4; inc = floor(sqrt(n))). */
@@ -99,6 +111,7 @@ int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
  * "num_threads"/"block_width": the NUM_THREADS / BLOCK_WIDTH command-line knobs of the
  * reference CUDA program (code/CUDA/cg_main.cc:21-25), mapped onto threads per CTA and
  * column-tile width of the mat-vec; "graph": 0/1 CUDA-graph replay of the iteration;
+ * "exchange": 0 ncclAllGather / 1 fused peer stores (see cgb_exchange_import);
  * "transposed": the reference's true/false kernel switch (accepted, A is symmetric). */
 int cgb_set_option(cgb_ctx *ctx, const char *key, int64_t value);
 int cgb_get_option(cgb_ctx *ctx, const char *key, int64_t *value);

@@ -1,0 +1,175 @@
+"""Multi-GPU parity (needs >= 2 B200s on the box: `gpurun --gpus 2 -- python -m pytest tests -m gpu`).
+
+Row-sharded A, one rank per GPU, the two exchanges -- ncclAllGather and the exchange fused into
+the mat-vec kernel (peer stores + flags) -- against the CPU oracle's emulated-rank solve, bit
+for bit (partial sums combined in rank order make the P-rank run reproducible).
+Ranks are threads of this process here (peer access); the one-process-per-GPU path (CUDA IPC)
+is covered by test_torchrun_two_ranks and by bench.py --gpus N.
+"""
+import json
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu(cgb):
+    try:
+        return cgb.device_count()
+    except cgb.CgbError:
+        return 0
+
+
+def _run_ranks(G, fn):
+    """fn(rank) on G threads (ctypes releases the GIL, the collective steps overlap)."""
+    out, err = [None] * G, []
+
+    def body(r):
+        try:
+            out[r] = fn(r)
+        except BaseException as e:  # noqa: BLE001 - reported below
+            err.append((r, e))
+
+    th = [threading.Thread(target=body, args=(r,)) for r in range(G)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in th), "a rank is stuck"
+    if err:
+        raise err[0][1]
+    return out
+
+
+def _solve_sharded(cgb, O, n, G, max_iter, exchange, setup=None, variant=None):
+    b = O.init_source_term(n)
+    ctxs = [cgb.Context(n, r, G, r) for r in range(G)]
+    try:
+        uid = cgb.unique_id()
+        _run_ranks(G, lambda r: ctxs[r].comm_init(uid))
+        blobs = [c.exchange_export() for c in ctxs]
+        for c in ctxs:
+            c.exchange_import(blobs)
+            c.set_option("exchange", exchange)
+            if variant is not None:
+                c.set_option("gemv_variant", variant)
+
+        def rank_body(r):
+            c = ctxs[r]
+            if setup is None:
+                c.generate_lap2d()
+            else:
+                setup(c)
+            c.set_rhs(b)
+            x = np.zeros(n)
+            info, hist = c.solve(x, max_iter=max_iter, tol=1e-10, history=True)
+            nx, rr = c.residual_check()
+            return x, info, hist, nx, rr
+
+        res = _run_ranks(G, rank_body)
+        nblk = ctxs[0].layout().nblk
+    finally:
+        for c in ctxs:
+            c.close()
+    return res, nblk, b
+
+
+@pytest.mark.parametrize("exchange", [0, 1], ids=["nccl", "fused"])
+@pytest.mark.parametrize("n,max_iter", [(1024, 1024), (1001, 120), (2050, 200)])
+def test_two_gpu_solve_bitwise_vs_emulated_ranks(cgb, O, n, max_iter, exchange):
+    if _ngpu(cgb) < 2:
+        pytest.skip("needs 2 GPUs")
+    G = 2
+    res, nblk, b = _solve_sharded(cgb, O, n, G, max_iter, exchange)
+    ref = O.solve(O.generate_lap2d(n), b, max_iter=max_iter, nranks=G, nblk=nblk)
+    for r, (x, info, hist, nx, rr) in enumerate(res):
+        assert info.k == ref.k and bool(info.converged) == ref.converged, r
+        assert np.array_equal(hist, ref.hist), r
+        assert np.array_equal(x, ref.x), r            # every rank ends with the full x
+        assert nx == ref.norm_x and rr == ref.rel_resid, r
+
+
+@pytest.mark.parametrize("exchange", [0, 1], ids=["nccl", "fused"])
+def test_all_gpus_match_one_gpu_within_tolerance(cgb, O, golden_dir, exchange):
+    """G = every GPU on the box vs the reference golden run (k +-1, 1e-10 / 1e-9)."""
+    from parity_util import check_against_reference
+    G = _ngpu(cgb)
+    if G < 2:
+        pytest.skip("needs >= 2 GPUs")
+    g = np.load(os.path.join(golden_dir, "gen_n4096.npz"))
+    n = int(g["n"])
+    res, nblk, b = _solve_sharded(cgb, O, n, G, n, exchange)
+    for x, info, hist, nx, rr in res:
+        check_against_reference(info.k, hist, x, g, "openblas", "gen_n4096 G=%d" % G)
+    ref = O.solve(O.generate_lap2d(n), b, max_iter=n, nranks=G, nblk=nblk)
+    assert res[0][1].k == ref.k and np.array_equal(res[0][2], ref.hist)
+
+
+def test_two_gpu_gemv_hook_and_remainder_shard(cgb, O):
+    """cgb_gemv on sharded ranks: each rank returns its own rows; the p'Ap total is the
+    rank-ordered deterministic sum on every rank.  n = 1003 gives the last rank the remainder."""
+    if _ngpu(cgb) < 2:
+        pytest.skip("needs 2 GPUs")
+    n, G = 1003, 2
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((n, n))
+    p = rng.standard_normal(n)
+    y_ref = O.gemv(A, p)
+    for exchange in (0, 1):
+        ctxs = [cgb.Context(n, r, G, r) for r in range(G)]
+        try:
+            uid = cgb.unique_id()
+            _run_ranks(G, lambda r: ctxs[r].comm_init(uid))
+            blobs = [c.exchange_export() for c in ctxs]
+            for c in ctxs:
+                c.exchange_import(blobs)
+                c.set_option("exchange", exchange)
+
+            def body(r):
+                ctxs[r].set_matrix_rows(A)
+                return ctxs[r].gemv(p, want_partials=True)
+
+            res = _run_ranks(G, body)
+            starts, counts = cgb.partition(n, G)
+            nblk = ctxs[0].layout().nblk
+            parts = []
+            for r in range(G):
+                y, bp, pap = res[r]
+                assert np.array_equal(y, y_ref[starts[r]:starts[r] + counts[r]])
+                q = (p * y_ref)[starts[r]:starts[r] + counts[r]]
+                bp_ref = np.array([O.det_sum(q[slice(*O.block_range(counts[r], nblk, c))]) for c in range(nblk)])
+                assert np.array_equal(bp, bp_ref)
+                parts.append(bp_ref)
+            total = O.det_sum(np.concatenate(parts))
+            assert res[0][2] == total and res[1][2] == total
+        finally:
+            for c in ctxs:
+                c.close()
+
+
+def test_torchrun_two_ranks(cgb, O, tmp_path):
+    """One process per GPU (torchrun, NCCL + CUDA IPC wiring), both exchanges, vs the oracle."""
+    if _ngpu(cgb) < 2:
+        pytest.skip("needs 2 GPUs")
+    out = tmp_path / "mp.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29731",
+           os.path.join(ROOT, "tests", "mp_solve_worker.py"), "--size", "1536", "--max-iter", "150",
+           "--out", str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = json.loads(out.read_text())
+    n = 1536
+    b = O.init_source_term(n)
+    ref = O.solve(O.generate_lap2d(n), b, max_iter=150, nranks=2, nblk=got["nblk"])
+    for mode in ("nccl", "fused"):
+        assert got[mode]["k"] == ref.k
+        assert np.array_equal(np.array(got[mode]["hist"]), ref.hist), mode
+        assert np.array_equal(np.array(got[mode]["x"]), ref.x), mode
+        assert got[mode]["ranks_agree"], mode
