@@ -18,6 +18,7 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
@@ -276,6 +277,19 @@ int build_graph(cgb_ctx *c)
     c->graph = g;
     CK(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
     c->graph_tol = c->tol; // tol and the history pointer are baked into the captured arguments
+    return CGB_OK;
+}
+
+// Which gather buffer the next mat-vec writes / the consumers read.  ncclAllGather always works
+// in buffer 0; a fused run that follows starts in buffer 1, so a peer that is still reading
+// buffer 0 of the previous run is never overwritten.
+int set_ctl_bufs(cgb_ctx *c, int wbuf, int rbuf)
+{
+    const int v[2] = {wbuf, rbuf};
+    static_assert(offsetof(Ctl, rbuf) == offsetof(Ctl, wbuf) + sizeof(int), "wbuf/rbuf must be adjacent");
+    CK(cudaMemcpyAsync(reinterpret_cast<char *>(c->ctl) + offsetof(Ctl, wbuf), v, sizeof v,
+                       cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return CGB_OK;
 }
 
@@ -547,7 +561,7 @@ extern "C" int cgb_exchange_import(cgb_ctx *c, const void *blobs)
     c->p2p_ready = true;
     c->opt_exchange = 1;
     drop_graph(c);
-    return CGB_OK;
+    return set_ctl_bufs(c, 1, 0);
 }
 
 // ------------------------------------------------------------------ inputs
@@ -708,6 +722,11 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
             return fail(CGB_ERR_STATE, "exchange = 1 needs cgb_exchange_import first");
         if (c->world > 1 && value == 0 && !c->comm)
             return fail(CGB_ERR_STATE, "exchange = 0 needs cgb_comm_init first");
+        if (c->opt_exchange != (int)value && c->world > 1) {
+            int rc = use_device(c);
+            if (rc) return rc;
+            if ((rc = set_ctl_bufs(c, value == 1 ? 1 : 0, 0))) return rc;
+        }
         c->opt_exchange = (int)value;
         drop_graph(c);
     } else if (k == "num_threads") {
