@@ -9,9 +9,10 @@
 // data in an identical order: bitwise equal on all ranks without any all-reduce.
 // Two implementations of that exchange (option "exchange"):
 //   1 (default once cgb_exchange_import was called)  FUSED: the mat-vec kernel stores every
-//     finished row straight into all peers' gather buffers over NVLink (peer-mapped memory,
-//     cudaIpc across processes) and its last CTA raises a flag on every rank; the x/r update
-//     kernel spins on its local flags.  No collective kernel, nothing between the two launches.
+//     finished row straight into all ranks' gather buffers over NVLink (peer-mapped memory,
+//     cudaIpc across processes) as self-flagging 16-byte LL entries {lo, tag, hi, tag}; the
+//     x/r update kernel polls exactly the entries it reads.  No fence, no flag, no collective
+//     kernel, nothing between the two launches.
 //   0  ncclAllGather (in place) between the two kernels -- the baseline to beat.
 #include "../../include/cgb200.h"
 #include "cgb_kernels.h"
@@ -113,12 +114,13 @@ struct cgb_ctx {
 
     double *A = nullptr, *p = nullptr, *r = nullptr, *x = nullptr, *b = nullptr;
     double *apx = nullptr, *rrpart = nullptr, *scratch = nullptr, *hist = nullptr, *sink = nullptr;
-    // gather buffers: apx = [2][world][slot_cap] doubles followed by the Ctl words
+    // apx: plain gather buffer [world][slot_cap] doubles.  ll: fused-mode LL buffers
+    // [2][world][slot_cap] x 16 B, the allocation peers map; ctl: local control words.
     long long bufstride = 0;
-    size_t apx_bytes = 0;
+    size_t ll_bytes = 0;
+    uint4 *ll = nullptr;
     Ctl *ctl = nullptr;
-    double *peer_base[kMaxWorld] = {};
-    Ctl *peer_ctl[kMaxWorld] = {};
+    uint4 *peer_ll[kMaxWorld] = {};
     void *ipc_opened[kMaxWorld] = {};
     bool p2p_ready = false;
     int opt_exchange = 0; // 0 = ncclAllGather, 1 = fused peer stores
@@ -160,6 +162,7 @@ Gather make_gather(const cgb_ctx *c)
     g.world = c->world;
     g.nblk = c->nblk;
     g.bufstride = c->bufstride;
+    g.ll = c->ll;
     g.ctl = c->ctl;
     g.p2p = (c->world > 1 && c->opt_exchange == 1) ? 1 : 0;
     return g;
@@ -178,10 +181,7 @@ GemvArgs make_gemv_args(const cgb_ctx *c, const double *v, int advance)
     a.rank = c->rank;
     a.world = c->world;
     a.p2p = (c->world > 1 && c->opt_exchange == 1) ? 1 : 0;
-    for (int g = 0; g < kMaxWorld; ++g) {
-        a.peer_base[g] = c->peer_base[g];
-        a.peer_ctl[g] = c->peer_ctl[g];
-    }
+    for (int g = 0; g < kMaxWorld; ++g) a.peer_ll[g] = c->peer_ll[g];
     a.ld = c->ld;
     a.rows = c->rows;
     a.row0 = c->row0;
@@ -280,31 +280,20 @@ int build_graph(cgb_ctx *c)
     return CGB_OK;
 }
 
-// Which gather buffer the next mat-vec writes / the consumers read.  ncclAllGather always works
-// in buffer 0; a fused run that follows starts in buffer 1, so a peer that is still reading
-// buffer 0 of the previous run is never overwritten.
-int set_ctl_bufs(cgb_ctx *c, int wbuf, int rbuf)
-{
-    const int v[2] = {wbuf, rbuf};
-    static_assert(offsetof(Ctl, rbuf) == offsetof(Ctl, wbuf) + sizeof(int), "wbuf/rbuf must be adjacent");
-    CK(cudaMemcpyAsync(reinterpret_cast<char *>(c->ctl) + offsetof(Ctl, wbuf), v, sizeof v,
-                       cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return CGB_OK;
-}
-
 bool exchange_configured(const cgb_ctx *c)
 {
     return c->world == 1 || (c->opt_exchange == 1 ? c->p2p_ready : c->comm != nullptr);
 }
 
-// the gather buffer the consumers currently read (hooks that memcpy out of it)
-int current_rbuf(cgb_ctx *c, const double **base)
+// Hooks that read the gathered result with memcpys: in fused mode first consume the running
+// exchange into the plain buffer (this also advances the epoch, like every consumer kernel).
+int collect_for_host(cgb_ctx *c)
 {
-    Ctl h;
-    CK(cudaMemcpyAsync(&h, c->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    *base = c->apx + (long long)h.rbuf * c->bufstride;
+    const Gather g = make_gather(c);
+    if (g.p2p) {
+        CK(launch_exchange_collect(c->apx, g, c->stream));
+        c->kernel_launches += 1;
+    }
     return CGB_OK;
 }
 
@@ -415,11 +404,15 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
     CKB(cudaMalloc(&c->x, vec_bytes));
     CKB(cudaMalloc(&c->b, vec_bytes));
     c->bufstride = (long long)c->world * c->slot_cap;
-    c->apx_bytes = (size_t)2 * c->bufstride * sizeof(double) + sizeof(Ctl);
-    CKB(cudaMalloc(&c->apx, c->apx_bytes));
-    c->ctl = reinterpret_cast<Ctl *>(c->apx + 2 * c->bufstride);
-    c->peer_base[rank] = c->apx;
-    c->peer_ctl[rank] = c->ctl;
+    CKB(cudaMalloc(&c->apx, (size_t)c->bufstride * sizeof(double)));
+    CKB(cudaMalloc(&c->ctl, sizeof(Ctl)));
+    if (world > 1) {
+        c->ll_bytes = (size_t)2 * c->bufstride * sizeof(uint4);
+        CKB(cudaMalloc(&c->ll, c->ll_bytes));
+        CKB(cudaMemsetAsync(c->ll, 0, c->ll_bytes, c->stream)); // tag 0 is never used
+        c->peer_ll[rank] = c->ll;
+    }
+    CKB(cudaMemsetAsync(c->ctl, 0, sizeof(Ctl), c->stream));
     CKB(cudaMalloc(&c->rrpart, (size_t)c->nchunks * sizeof(double)));
     CKB(cudaMalloc(&c->scratch, (size_t)(3 * c->nchunks + 8) * sizeof(double)));
     CKB(cudaMalloc(&c->sink, 64));
@@ -433,7 +426,7 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
     CKB(cudaMemsetAsync(c->r, 0, vec_bytes, c->stream));
     CKB(cudaMemsetAsync(c->x, 0, vec_bytes, c->stream));
     CKB(cudaMemsetAsync(c->b, 0, vec_bytes, c->stream));
-    CKB(cudaMemsetAsync(c->apx, 0, c->apx_bytes, c->stream));
+    CKB(cudaMemsetAsync(c->apx, 0, (size_t)c->bufstride * sizeof(double), c->stream));
     CKB(cudaMemsetAsync(c->rrpart, 0, (size_t)c->nchunks * sizeof(double), c->stream));
     CKB(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
     CKB(cudaStreamSynchronize(c->stream));
@@ -456,6 +449,8 @@ extern "C" int cgb_destroy(cgb_ctx *c)
     for (double *p : bufs)
         if (p) cudaFree(p);
     if (c->st) cudaFree(c->st);
+    if (c->ll) cudaFree(c->ll);
+    if (c->ctl) cudaFree(c->ctl);
     if (c->h_done) cudaFreeHost(c->h_done);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -516,9 +511,9 @@ extern "C" int cgb_exchange_export(cgb_ctx *c, void *blob_out)
     b.device = c->device;
     b.rank = c->rank;
     b.world = c->world;
-    b.ptr = (uint64_t)(uintptr_t)c->apx;
-    b.bytes = c->apx_bytes;
-    CK(cudaIpcGetMemHandle(&b.handle, c->apx));
+    b.ptr = (uint64_t)(uintptr_t)c->ll;
+    b.bytes = c->ll_bytes;
+    if (c->ll) CK(cudaIpcGetMemHandle(&b.handle, c->ll));
     memset(blob_out, 0, CGB_EXCHANGE_BLOB_BYTES);
     memcpy(blob_out, &b, sizeof b);
     return CGB_OK;
@@ -536,7 +531,7 @@ extern "C" int cgb_exchange_import(cgb_ctx *c, const void *blobs)
     for (int g = 0; g < c->world; ++g) {
         XchBlob b;
         memcpy(&b, base + (size_t)g * CGB_EXCHANGE_BLOB_BYTES, sizeof b);
-        if (b.magic != kXchMagic || b.rank != g || b.world != c->world || b.bytes != c->apx_bytes)
+        if (b.magic != kXchMagic || b.rank != g || b.world != c->world || b.bytes != c->ll_bytes)
             return fail(CGB_ERR_INVALID, "exchange blob %d does not match this context "
                         "(rank %d world %d bytes %llu)", g, b.rank, b.world, (unsigned long long)b.bytes);
         if (g == c->rank) continue;
@@ -555,13 +550,12 @@ extern "C" int cgb_exchange_import(cgb_ctx *c, const void *blobs)
             CK(cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess));
             c->ipc_opened[g] = ptr;
         }
-        c->peer_base[g] = static_cast<double *>(ptr);
-        c->peer_ctl[g] = reinterpret_cast<Ctl *>(c->peer_base[g] + 2 * c->bufstride);
+        c->peer_ll[g] = static_cast<uint4 *>(ptr);
     }
     c->p2p_ready = true;
     c->opt_exchange = 1;
     drop_graph(c);
-    return set_ctl_bufs(c, 1, 0);
+    return CGB_OK;
 }
 
 // ------------------------------------------------------------------ inputs
@@ -722,11 +716,6 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
             return fail(CGB_ERR_STATE, "exchange = 1 needs cgb_exchange_import first");
         if (c->world > 1 && value == 0 && !c->comm)
             return fail(CGB_ERR_STATE, "exchange = 0 needs cgb_comm_init first");
-        if (c->opt_exchange != (int)value && c->world > 1) {
-            int rc = use_device(c);
-            if (rc) return rc;
-            if ((rc = set_ctl_bufs(c, value == 1 ? 1 : 0, 0))) return rc;
-        }
         c->opt_exchange = (int)value;
         drop_graph(c);
     } else if (k == "num_threads") {
@@ -976,14 +965,9 @@ extern "C" int cgb_gemv(cgb_ctx *c, const double *v_host, double *y_host, double
     if (!exchange_configured(c)) return fail(CGB_ERR_STATE, "world > 1 but no exchange is configured");
     if ((rc = launch_matvec(c, c->p, 0, c->variant))) return rc;
     if ((rc = launch_gather(c))) return rc;
+    if ((rc = collect_for_host(c))) return rc;
     const Gather gth = make_gather(c);
-    if (gth.p2p) {
-        CK(launch_exchange_wait(gth, c->stream));
-        c->kernel_launches += 1;
-    }
-    const double *rb = nullptr;
-    if ((rc = current_rbuf(c, &rb))) return rc;
-    const double *mine = rb + (long long)c->rank * c->slot;
+    const double *mine = c->apx + (long long)c->rank * c->slot;
     if (y_host) CK(cudaMemcpyAsync(y_host, mine, (size_t)c->rows * 8, cudaMemcpyDeviceToHost, c->stream));
     if (block_partials)
         CK(cudaMemcpyAsync(block_partials, mine + c->maxrows, (size_t)c->nblk * 8, cudaMemcpyDeviceToHost,
@@ -1024,13 +1008,20 @@ extern "C" int cgb_bench_gemv(cgb_ctx *c, int variant, int reps, float *ms_avg)
     if (!c->matrix_set) return fail(CGB_ERR_STATE, "matrix not set");
     if (variant < 0) variant = c->variant;
     if (variant >= gemv_variant_count() || reps < 1) return fail(CGB_ERR_INVALID, "bad variant / reps");
+    if (!exchange_configured(c)) return fail(CGB_ERR_STATE, "world > 1 but no exchange is configured");
+    if (gemv_variant(variant).ctas_per_sm * c->sm_count != c->nblk && c->world > 1)
+        return fail(CGB_ERR_INVALID, "with world > 1 only variants with the configured grid can be timed");
     CK(cudaMemsetAsync(&c->st->done, 0, sizeof(int), c->stream));
     if ((rc = launch_matvec(c, c->p, 0, variant))) return rc; // warm-up
     CK(cudaEventRecord(c->ev0, c->stream));
     for (int i = 0; i < reps; ++i)
         if ((rc = launch_matvec(c, c->p, 0, variant))) return rc;
     CK(cudaEventRecord(c->ev1, c->stream));
+    // fused mode: the launches above all carried the same tag; consume it so that the next
+    // exchange starts from a fresh tag on every rank
+    if ((rc = collect_for_host(c))) return rc;
     CK(cudaEventSynchronize(c->ev1));
+    CK(cudaStreamSynchronize(c->stream));
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
     if (ms_avg) *ms_avg = t / reps;

@@ -24,43 +24,44 @@ struct State {
     int pad;
 };
 
-// Control words of the mat-vec exchange, in device memory next to the gather buffers (and, in
-// P2P mode, written by the peers over NVLink).
+// Control words of the fused exchange (P2P mode), local to each rank.
 struct Ctl {
-    unsigned long long flags[kMaxWorld]; // flags[g] = number of exchanges rank g has delivered here
-    unsigned long long epoch;            // exchanges this rank has sent
-    unsigned int arrive;                 // CTAs of the running mat-vec that have finished
-    int wbuf;                            // gather buffer the next mat-vec writes   (P2P: alternates)
-    int rbuf;                            // gather buffer the consumers read        (P2P: alternates)
-    int pad;
+    unsigned long long epoch; // exchanges consumed so far; the running one carries tag epoch + 1
+    unsigned int arrive;      // blocks of the running consumer kernel that have finished reading
+    unsigned int pad;
 };
 
-// Geometry of the gathered mat-vec result: rank g owns slot g of `slot` doubles,
+// Geometry of the gathered mat-vec result: rank g owns slot g of `slot` entries,
 // [0, rows_g) = its Ap rows, [maxrows, maxrows + nblk) = its p'Ap block partials.
-// Two such buffers (`bufstride` doubles apart) exist; only P2P mode uses the second.
+//   plain buffer (`apx`, doubles)  : 1 GPU, ncclAllGather mode, staging for the test hooks
+//   LL buffers (`ll`, 16 B entries): fused mode.  An entry is {lo32, tag, hi32, tag}: the value
+//       carries its own arrival flag (the tag of the exchange), so the producer needs no fence
+//       and no separate flag store, and the consumer polls exactly the data it needs -- the
+//       LL protocol of NCCL, applied to fp64.  Two buffers (tag parity): ranks can be at most
+//       one exchange apart.
 struct Gather {
     long long n_loc;   // rows of every rank but the last (N / world)
-    long long slot;    // doubles per rank slot
+    long long slot;    // entries per rank slot
     long long maxrows; // rows of the last rank (the largest shard)
-    long long bufstride;
-    const Ctl *ctl;
+    long long bufstride; // entries per LL buffer (world * slot capacity)
+    const uint4 *ll;   // this rank's LL buffers (peers write into them over NVLink)
+    Ctl *ctl;
     int world;
     int nblk;
-    int p2p;           // 1: wait for the peers' flags before reading (fused exchange)
+    int p2p;           // 1: fused mode
 };
 
 struct GemvArgs {
     const double *A;      // rows x ld shard, zero-padded columns
     const double *v;      // input vector, ld doubles, zero-padded
-    double *base;         // local gather buffers (2 x bufstride doubles)
-    double *peer_base[kMaxWorld]; // P2P mode: every rank's gather buffers (self included)
-    Ctl *ctl;
-    Ctl *peer_ctl[kMaxWorld];
+    double *base;         // local plain gather buffer
+    uint4 *peer_ll[kMaxWorld]; // fused mode: every rank's LL buffers (self included), peer-mapped
+    const Ctl *ctl;
     long long bufstride;
     long long slot_off;   // rank * slot: where this rank's slot starts inside a buffer
     int rank;
     int world;
-    int p2p;              // 1: store rows + partials straight into every peer, then raise flags
+    int p2p;              // 1: store rows + partials straight into every rank's LL buffer
     long long ld;
     long long rows;
     long long row0;       // global index of the shard's first row (index into v)
@@ -128,46 +129,74 @@ __device__ __forceinline__ double block_chunk256(double v, double *wsum, int tid
     return t;
 }
 
-// ------------------------------------------------------------------ exchange (P2P mode)
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
+// ------------------------------------------------------------------ exchange (fused mode)
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
-// Consumer side of the fused exchange: block until every rank has delivered the mat-vec result
-// this rank has itself just sent (epoch).  Threads 0..world-1 each poll one LOCAL flag; the
-// wait is bounded (a dead peer faults the launch instead of hanging the GPU).  Ends with a
-// block barrier, so it must be called by all threads of the block.
-__device__ __forceinline__ void exchange_wait(const Gather &g, int tid)
+// producer: one 16-byte store {lo, tag, hi, tag}; correct even if it tears into two 8-byte halves
+__device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned tag)
+{
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(tag), "r"(hi),
+                 "r"(tag)
+                 : "memory");
+}
+// consumer: poll the entry until both halves carry the tag.  Bounded: a dead peer faults the
+// launch (trap) instead of hanging the GPU.
+__device__ __forceinline__ double ll_load(const uint4 *src, unsigned tag)
+{
+    unsigned lo, f0, hi, f1;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src) : "memory");
+    if (f0 != tag || f1 != tag) {
+        const unsigned long long t0 = globaltimer_ns();
+        do {
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src) : "memory");
+            if (globaltimer_ns() - t0 > 20000000000ULL) __trap();
+        } while (f0 != tag || f1 != tag);
+    }
+    return __hiloint2double((int)hi, (int)lo);
+}
+// tag of the exchange the running mat-vec produces / the running consumer kernel reads.
+// ctl->epoch only changes in exchange_consumed(), never while either of them is reading it.
+__device__ __forceinline__ unsigned exchange_tag(const Ctl *ctl) { return (unsigned)(ctl->epoch + 1ULL); }
+
+// The consumers' view of the gathered result.
+struct GatherView {
+    const double *plain;
+    const uint4 *ll;
+    unsigned tag;
+    int p2p;
+};
+__device__ __forceinline__ GatherView gather_view(const double *apx, const Gather &g)
+{
+    GatherView v;
+    v.plain = apx;
+    v.p2p = g.p2p;
+    v.tag = g.p2p ? exchange_tag(g.ctl) : 0u;
+    v.ll = g.ll + (long long)(v.tag & 1u) * g.bufstride;
+    return v;
+}
+__device__ __forceinline__ double gather_read(const GatherView &v, long long idx)
+{
+    return v.p2p ? ll_load(v.ll + idx, v.tag) : v.plain[idx];
+}
+// Called by ALL threads of every block of a consumer kernel after its last gather_read: the
+// last block to finish advances the epoch, so the next mat-vec tags (and double-buffers) anew.
+__device__ __forceinline__ void exchange_consumed(const Gather &g, int tid)
 {
     if (g.p2p) {
-        if (tid < g.world) {
-            const unsigned long long want = g.ctl->epoch;
-            if (ld_acquire_sys_u64(&g.ctl->flags[tid]) < want) {
-                const unsigned long long t0 = globaltimer_ns();
-                while (ld_acquire_sys_u64(&g.ctl->flags[tid]) < want) {
-                    if (globaltimer_ns() - t0 > 20000000000ULL) __trap();
-                }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned t = atomicAdd(&g.ctl->arrive, 1u);
+            if (t == gridDim.x - 1) {
+                g.ctl->arrive = 0;
+                g.ctl->epoch = g.ctl->epoch + 1ULL;
             }
         }
-        __syncthreads();
     }
-}
-// base of the gather buffer the consumers read
-__device__ __forceinline__ const double *gather_rbuf(const double *apx, const Gather &g)
-{
-    return apx + (long long)g.ctl->rbuf * g.bufstride;
 }
 
 __device__ __forceinline__ long long gather_index(const Gather &g, long long i)

@@ -48,9 +48,9 @@ cudaError_t launch_dot(const double *a, const double *b, long long n, double *sc
 // total of the block partials of all ranks (tests): out[0] = p'Ap
 cudaError_t launch_sum_partials(const double *apx, const Gather &g, double *out, cudaStream_t s);
 
-// P2P mode: block the stream until every rank's mat-vec result has landed (hooks only; the
-// kernels of the iteration wait by themselves)
-cudaError_t launch_exchange_wait(const Gather &g, cudaStream_t s);
+// fused mode, hooks only: consume the running exchange into the plain gather buffer `apx`
+// (the kernels of the iteration read the LL entries directly)
+cudaError_t launch_exchange_collect(double *apx, const Gather &g, cudaStream_t s);
 
 // ---- matrix construction (vec.cu) --------------------------------------------------
 // generate_lap2d_matrix (cg.cc:159-188) into the shard

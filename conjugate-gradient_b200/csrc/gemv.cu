@@ -41,37 +41,17 @@ __device__ __forceinline__ void advance_state(const GemvArgs &a, int lane)
 }
 
 // One result (a row of Ap, or the block partial of p'Ap) into the gather buffer: locally, or --
-// fused exchange -- straight into the same place on every rank over NVLink (peer stores).
-__device__ __forceinline__ void store_out(const GemvArgs &a, long long off, double v)
+// fused exchange -- as a self-flagging LL entry straight into every rank's buffer over NVLink
+// (peer stores).  That store IS the all-gather: no fence, no flag, no collective kernel.
+__device__ __forceinline__ void store_out(const GemvArgs &a, long long plain_off, long long ll_off,
+                                          unsigned tag, double v)
 {
     if (!a.p2p) {
-        a.base[off] = v;
+        a.base[plain_off] = v;
     } else {
 #pragma unroll
         for (int g = 0; g < kMaxWorld; ++g)
-            if (g < a.world) a.peer_base[g][off] = v;
-    }
-}
-
-// Fused exchange, producer side.  Called by ONE thread per CTA after all of the CTA's results
-// were stored (and fenced): the last CTA to arrive publishes the new epoch to every rank.
-// This is the whole "all-gather": no collective kernel, no host involvement.
-__device__ __forceinline__ void exchange_signal(const GemvArgs &a, int wb)
-{
-    __threadfence_system();
-    const unsigned prev = atomicAdd(&a.ctl->arrive, 1u);
-    if (prev == gridDim.x - 1) {
-        __threadfence_system();
-        Ctl *ctl = a.ctl;
-        ctl->arrive = 0;
-        const unsigned long long e = ctl->epoch + 1;
-        ctl->epoch = e;
-        ctl->rbuf = wb;
-        ctl->wbuf = wb ^ 1;
-        __threadfence_system();
-#pragma unroll
-        for (int g = 0; g < kMaxWorld; ++g)
-            if (g < a.world) st_release_sys_u64(&a.peer_ctl[g]->flags[a.rank], e);
+            if (g < a.world) ll_store(a.peer_ll[g] + ll_off, v, tag);
     }
 }
 
@@ -95,8 +75,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
     const long long r0 = (long long)c * a.rows / nblk;
     const long long r1 = (long long)(c + 1) * a.rows / nblk;
     const int nrows = (int)(r1 - r0);
-    const int wb = a.p2p ? a.ctl->wbuf : 0;        // gather buffer of this launch
-    const long long obase = (long long)wb * a.bufstride + a.slot_off;
+    const unsigned tag = a.p2p ? exchange_tag(a.ctl) : 0u; // fused mode: tag + buffer of this exchange
+    const long long obase = a.slot_off;
+    const long long lbase = (long long)(tag & 1u) * a.bufstride + a.slot_off;
     const int nb = (nrows + TR - 1) / TR;          // row blocks, balanced below
     const int ntc = (int)((a.ld + TC - 1) / TC);   // column tiles
 
@@ -193,20 +174,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
                     const double y = warp_butterfly(__dadd_rn(acc0[s], acc1[s]));
                     if (lane == 0) {
                         const long long li = rb0 + warp + s * CW;
-                        store_out(a, obase + li, y);
+                        store_out(a, obase + li, lbase + li, tag, y);
                         qs[li - r0] = __dmul_rn(prow[s], y);
                     }
                 }
             }
         }
-        if (a.p2p && lane == 0) __threadfence_system(); // this warp's peer stores, before the signal
         named_bar_sync(1, CW * 32);
         if (warp == 0) {
             const double bp = warp_det_sum(qs, nrows, lane);
-            if (lane == 0) {
-                store_out(a, obase + a.maxrows + c, bp);
-                if (a.p2p) exchange_signal(a, wb);
-            }
+            if (lane == 0) store_out(a, obase + a.maxrows + c, lbase + a.maxrows + c, tag, bp);
         }
     }
 }
@@ -226,8 +203,9 @@ __global__ void __launch_bounds__(W * 32) gemv_ldg_kernel(const GemvArgs a)
     const long long r1 = (long long)(c + 1) * a.rows / nblk;
     const int nrows = (int)(r1 - r0);
     const int ng = (nrows + RPW - 1) / RPW;
-    const int wb = a.p2p ? a.ctl->wbuf : 0;
-    const long long obase = (long long)wb * a.bufstride + a.slot_off;
+    const unsigned tag = a.p2p ? exchange_tag(a.ctl) : 0u;
+    const long long obase = a.slot_off;
+    const long long lbase = (long long)(tag & 1u) * a.bufstride + a.slot_off;
     const long long nq = a.ld >> 1;
     const double2 *v2 = reinterpret_cast<const double2 *>(a.v);
 
@@ -269,20 +247,16 @@ __global__ void __launch_bounds__(W * 32) gemv_ldg_kernel(const GemvArgs a)
                 const double y = warp_butterfly(__dadd_rn(acc0[s], acc1[s]));
                 if (lane == 0) {
                     const long long li = rg0 + s;
-                    store_out(a, obase + li, y);
+                    store_out(a, obase + li, lbase + li, tag, y);
                     qs[li - r0] = __dmul_rn(a.v[a.row0 + li], y);
                 }
             }
         }
     }
-    if (a.p2p && lane == 0) __threadfence_system();
     __syncthreads();
     if (warp == 0) {
         const double bp = warp_det_sum(qs, nrows, lane);
-        if (lane == 0) {
-            store_out(a, obase + a.maxrows + c, bp);
-            if (a.p2p) exchange_signal(a, wb);
-        }
+        if (lane == 0) store_out(a, obase + a.maxrows + c, lbase + a.maxrows + c, tag, bp);
     }
 }
 

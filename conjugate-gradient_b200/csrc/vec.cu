@@ -34,11 +34,10 @@ __global__ void __launch_bounds__(kChunk) init_residual_kernel(const VecArgs a)
     __shared__ double wsum[8];
     const int tid = threadIdx.x;
     const long long i = (long long)blockIdx.x * kChunk + tid;
-    exchange_wait(a.g, tid);
-    const double *apx = gather_rbuf(a.apx, a.g);
+    const GatherView gv = gather_view(a.apx, a.g);
     double v = 0.0;
     if (i < a.n) {
-        const double ap = apx[gather_index(a.g, i)];
+        const double ap = gather_read(gv, gather_index(a.g, i));
         const double rr = __fma_rn(-1.0, ap, a.b[i]); // daxpy(-1, Ap, r = b)   cg.cc:82
         a.r[i] = rr;
         a.p[i] = rr;                                  // p = r                  cg.cc:85
@@ -46,6 +45,7 @@ __global__ void __launch_bounds__(kChunk) init_residual_kernel(const VecArgs a)
     }
     const double t = block_chunk256(v, wsum, tid);
     if (tid == 0) a.rrpart[blockIdx.x] = t;
+    exchange_consumed(a.g, tid);
 }
 
 __global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a)
@@ -55,12 +55,13 @@ __global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a)
     __shared__ double sh_alpha;
     if (a.st->done) return;
     const int tid = threadIdx.x;
-    exchange_wait(a.g, tid);                 // fused exchange: the peers' rows have landed
-    const double *apx = gather_rbuf(a.apx, a.g);
+    // fused exchange: every read below polls its own LL entry until the owning rank's mat-vec
+    // has delivered it over NVLink -- this kernel may start while peers are still streaming A
+    const GatherView gv = gather_view(a.apx, a.g);
     const int total = a.g.world * a.g.nblk;
     for (int t = tid; t < total; t += kChunk) {
         const int r = t / a.g.nblk, c = t - r * a.g.nblk;
-        sh_part[t] = apx[(long long)r * a.g.slot + a.g.maxrows + c];
+        sh_part[t] = gather_read(gv, (long long)r * a.g.slot + a.g.maxrows + c);
     }
     __syncthreads();
     if (tid < 32) {
@@ -83,12 +84,13 @@ __global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a)
     if (i < a.n) {
         const double pi = a.p[i];
         a.x[i] = __fma_rn(alpha, pi, a.x[i]);                          // cg.cc:110
-        const double rn = __fma_rn(-alpha, apx[gather_index(a.g, i)], a.r[i]); // cg.cc:113
+        const double rn = __fma_rn(-alpha, gather_read(gv, gather_index(a.g, i)), a.r[i]); // cg.cc:113
         a.r[i] = rn;
         v = __dmul_rn(rn, rn);                                         // cg.cc:116
     }
     const double t = block_chunk256(v, wsum, tid);
     if (tid == 0) a.rrpart[blockIdx.x] = t;
+    exchange_consumed(a.g, tid);
 }
 
 __global__ void __launch_bounds__(kChunk) update_p_kernel(const VecArgs a, long long nchunks)
@@ -139,12 +141,11 @@ __global__ void __launch_bounds__(kChunk) debug_partials_kernel(const VecArgs a,
     __shared__ double wsum[8];
     const int tid = threadIdx.x;
     const long long i = (long long)blockIdx.x * kChunk + tid;
-    exchange_wait(a.g, tid);
-    const double *apx = gather_rbuf(a.apx, a.g);
+    const GatherView gv = gather_view(a.apx, a.g);
     double dd = 0.0, bb = 0.0, xx = 0.0;
     if (i < a.n) {
         const double bi = a.b[i], xi = a.x[i];
-        const double d = __fma_rn(-1.0, bi, apx[gather_index(a.g, i)]); // cg.cc:146-148
+        const double d = __fma_rn(-1.0, bi, gather_read(gv, gather_index(a.g, i))); // cg.cc:146-148
         dd = __dmul_rn(d, d);
         bb = __dmul_rn(bi, bi);
         xx = __dmul_rn(xi, xi);
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(kChunk) debug_partials_kernel(const VecArgs a,
     __syncthreads();
     t = block_chunk256(xx, wsum, tid);
     if (tid == 0) scratch[2 * nchunks + blockIdx.x] = t;
+    exchange_consumed(a.g, tid);
 }
 
 __global__ void __launch_bounds__(32) debug_final_kernel(const double *scratch, long long nchunks,
@@ -191,13 +193,29 @@ __global__ void __launch_bounds__(32) sum_kernel(const double *v, long long n, d
 
 __global__ void __launch_bounds__(32) sum_partials_kernel(const double *apx, const Gather g, double *out)
 {
-    exchange_wait(g, threadIdx.x);
-    const double s = warp_det_sum_partials(gather_rbuf(apx, g), g, threadIdx.x);
+    const double s = warp_det_sum_partials(apx, g, threadIdx.x);
     if (threadIdx.x == 0) out[0] = s;
 }
 
-// hooks that read the gather buffer with a memcpy wait for the exchange with this kernel
-__global__ void __launch_bounds__(32) exchange_wait_kernel(const Gather g) { exchange_wait(g, threadIdx.x); }
+// Fused mode, test hooks only: consume the running exchange into the plain buffer (every rank's
+// rows and block partials), so that memcpys and sum_partials_kernel can read it.
+__global__ void __launch_bounds__(kChunk) exchange_collect_kernel(double *apx, const Gather g)
+{
+    const int tid = threadIdx.x;
+    const GatherView gv = gather_view(apx, g);
+    const long long per = g.maxrows + g.nblk;
+    const long long total = (long long)g.world * per;
+    for (long long t = (long long)blockIdx.x * kChunk + tid; t < total; t += (long long)gridDim.x * kChunk) {
+        const int r = (int)(t / per);
+        const long long e = t - (long long)r * per;
+        const long long rows_r = (r == g.world - 1) ? g.maxrows : g.n_loc;
+        if (e < rows_r || e >= g.maxrows) {
+            const long long idx = (long long)r * g.slot + e;
+            apx[idx] = gather_read(gv, idx);
+        }
+    }
+    exchange_consumed(g, tid);
+}
 
 // generate_lap2d_matrix (cg.cc:159-188): every element of the shard is written once, two
 // columns per thread (128-bit stores); padding columns [n, ld) are zero.
@@ -296,9 +314,12 @@ cudaError_t launch_sum_partials(const double *apx, const Gather &g, double *out,
     return cudaGetLastError();
 }
 
-cudaError_t launch_exchange_wait(const Gather &g, cudaStream_t s)
+cudaError_t launch_exchange_collect(double *apx, const Gather &g, cudaStream_t s)
 {
-    exchange_wait_kernel<<<1, 32, 0, s>>>(g);
+    const long long total = (long long)g.world * (g.maxrows + g.nblk);
+    long long blocks = (total + kChunk - 1) / kChunk;
+    if (blocks > 296) blocks = 296;
+    exchange_collect_kernel<<<(int)blocks, kChunk, 0, s>>>(apx, g);
     return cudaGetLastError();
 }
 

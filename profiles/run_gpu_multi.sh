@@ -7,7 +7,7 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=index,name,clocks.max.sm --format=csv > $OUT/smi_g$G.txt
 nvidia-smi topo -m >> $OUT/smi_g$G.txt 2>&1
 if [ "$2" = "tests" ]; then
-  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_g$G.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu_g$G.log
+  timeout 900 python -m pytest tests -m gpu -q > $OUT/pytest_gpu_g$G.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu_g$G.log
 fi
 run_bench() { # gpus exchange tag extra...
   local g=$1 ex=$2 tag=$3; shift 3

@@ -21,6 +21,13 @@ def _run(args, env=None, timeout=300):
                           env=dict(os.environ, **(env or {})))
 
 
+def _step_line(stdout):
+    """The DEBUG line (NCCL may print its version banner on stdout when NCCL_DEBUG is set)."""
+    hits = [ln for ln in stdout.splitlines() if ln.startswith("\t[STEP")]
+    assert len(hits) == 1, stdout
+    return hits[0]
+
+
 def test_form1_generated(O, tmp_path):
     """cgsolver N outfile [max_iter]: DEBUG line identical to the oracle's, row `n,psize,seconds`
     appended (not truncated)."""
@@ -77,5 +84,5 @@ def test_multi_gpu_cli_psize_column(O, tmp_path, cgb):
         r = _run(["2048", str(out), "150"], env={"CGB_GPUS": "2", "CGB_EXCHANGE": mode})
         assert r.returncode == 0, r.stderr
         ref = O.solve(O.generate_lap2d(2048), O.init_source_term(2048), max_iter=150, nranks=2, nblk=148)
-        assert r.stdout.splitlines()[0] == O.debug_line(150, ref.rsold, ref.norm_x, ref.rel_resid)
+        assert _step_line(r.stdout) == O.debug_line(150, ref.rsold, ref.norm_x, ref.rel_resid)
     assert [row.split(",")[:2] for row in out.read_text().splitlines()] == [["2048", "2"]] * 2
