@@ -1008,9 +1008,13 @@ extern "C" int cgb_bench_gemv(cgb_ctx *c, int variant, int reps, float *ms_avg)
     if (!c->matrix_set) return fail(CGB_ERR_STATE, "matrix not set");
     if (variant < 0) variant = c->variant;
     if (variant >= gemv_variant_count() || reps < 1) return fail(CGB_ERR_INVALID, "bad variant / reps");
-    if (!exchange_configured(c)) return fail(CGB_ERR_STATE, "world > 1 but no exchange is configured");
-    if (gemv_variant(variant).ctas_per_sm * c->sm_count != c->nblk && c->world > 1)
-        return fail(CGB_ERR_INVALID, "with world > 1 only variants with the configured grid can be timed");
+    // A rank of a world > 1 without a configured exchange times its shard with local stores
+    // only (shape tuning on one GPU).  The gather geometry follows the timed variant.
+    const int keep_variant = c->variant;
+    if (variant != keep_variant) {
+        set_variant(c, variant);
+        drop_graph(c);
+    }
     CK(cudaMemsetAsync(&c->st->done, 0, sizeof(int), c->stream));
     if ((rc = launch_matvec(c, c->p, 0, variant))) return rc; // warm-up
     CK(cudaEventRecord(c->ev0, c->stream));
@@ -1022,6 +1026,7 @@ extern "C" int cgb_bench_gemv(cgb_ctx *c, int variant, int reps, float *ms_avg)
     if ((rc = collect_for_host(c))) return rc;
     CK(cudaEventSynchronize(c->ev1));
     CK(cudaStreamSynchronize(c->stream));
+    if (variant != keep_variant) set_variant(c, keep_variant);
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
     if (ms_avg) *ms_avg = t / reps;

@@ -272,6 +272,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32
         "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ void bulk_g2s_nohint(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -56,7 +56,7 @@ __device__ __forceinline__ void store_out(const GemvArgs &a, long long plain_off
 }
 
 // ------------------------------------------------------------------------------- TMA
-template <int CW, int RPW, int TC, int STAGES, int MINB>
+template <int CW, int RPW, int TC, int STAGES, int MINB, int POL>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const GemvArgs a)
 {
     constexpr int TR = CW * RPW;
@@ -107,9 +107,14 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
                 if (lane == 0) mbar_arrive_expect_tx(&full[stage], (unsigned)((nr + 1) * w * 8));
                 __syncwarp();
                 double *dstA = sA + (size_t)stage * TR * TC;
-                for (int j = lane; j < nr; j += 32)
-                    bulk_g2s(dstA + (size_t)j * TC, a.A + (rb0 + j) * a.ld + c0, (unsigned)(w * 8),
-                             &full[stage], pol_a);
+                for (int j = lane; j < nr; j += 32) {
+                    if (POL == 0)
+                        bulk_g2s(dstA + (size_t)j * TC, a.A + (rb0 + j) * a.ld + c0, (unsigned)(w * 8),
+                                 &full[stage], pol_a);
+                    else
+                        bulk_g2s_nohint(dstA + (size_t)j * TC, a.A + (rb0 + j) * a.ld + c0,
+                                        (unsigned)(w * 8), &full[stage]);
+                }
                 if (lane == 31)
                     bulk_g2s(sP + (size_t)stage * TC, a.v + c0, (unsigned)(w * 8), &full[stage], pol_p);
             }
@@ -286,19 +291,19 @@ __global__ void __launch_bounds__(512) read_stream_kernel(const double *A, long 
 // ------------------------------------------------------------------------------- table
 namespace {
 
-template <int CW, int RPW, int TC, int STAGES, int MINB>
+template <int CW, int RPW, int TC, int STAGES>
 size_t tma_smem(long long rows_per_cta)
 {
     return (size_t)STAGES * CW * RPW * TC * 8 + (size_t)STAGES * TC * 8 + 2 * STAGES * 8 +
            (size_t)rows_per_cta * 8;
 }
 
-template <int CW, int RPW, int TC, int STAGES, int MINB>
+template <int CW, int RPW, int TC, int STAGES, int MINB, int POL = 0>
 cudaError_t tma_launch(const GemvArgs &a, int nblk, cudaStream_t s)
 {
     const long long rpc = (a.rows + nblk - 1) / nblk;
-    const size_t smem = tma_smem<CW, RPW, TC, STAGES, MINB>(rpc);
-    auto k = gemv_tma_kernel<CW, RPW, TC, STAGES, MINB>;
+    const size_t smem = tma_smem<CW, RPW, TC, STAGES>(rpc);
+    auto k = gemv_tma_kernel<CW, RPW, TC, STAGES, MINB, POL>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<nblk, (CW + 1) * 32, smem, s>>>(a);
@@ -329,6 +334,11 @@ const GemvVariant kVariants[] = {
     {"tma_w16r1c512s3", 1, 544, tma_launch<16, 1, 512, 3, 1>},
     {"tma2_w4r2c512s3", 2, 160, tma_launch<4, 2, 512, 3, 2>},
     {"tma2_w8r1c256s6", 2, 288, tma_launch<8, 1, 256, 6, 2>},
+    {"tma_w8r1c1024s3", 1, 288, tma_launch<8, 1, 1024, 3, 1>},
+    {"tma_w4r2c1024s3", 1, 160, tma_launch<4, 2, 1024, 3, 1>},
+    {"tma_w16r2c256s3", 1, 544, tma_launch<16, 2, 256, 3, 1>},
+    {"tma2_w4r1c1024s3", 2, 160, tma_launch<4, 1, 1024, 3, 2>},
+    {"tma_w8r2c512s3_nohint", 1, 288, tma_launch<8, 2, 512, 3, 1, 1>},
     {"ldg_w8r4u2", 4, 256, ldg_launch<8, 4, 2>},
     {"ldg_w8r2u4", 4, 256, ldg_launch<8, 2, 4>},
     {"ldg_w16r4u2", 2, 512, ldg_launch<16, 4, 2>},

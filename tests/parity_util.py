@@ -18,10 +18,15 @@ def prefloor_length(h_ref):
     return int(below[0]) if len(below) else len(h_ref)
 
 
-def check_against_reference(k, hist, x, g, blas="openblas", label=""):
-    """g: a loaded tests/golden/*.npz."""
+def check_against_reference(k, hist, x, g, blas="openblas", label="", any_provider_k=False):
+    """g: a loaded tests/golden/*.npz.  any_provider_k: accept an iteration count within +-1 of
+    EITHER of the reference's own BLAS providers (OpenBLAS / naive loops).  The stopping rule
+    sits below fp64's attainable accuracy, so the count depends on the summation order --
+    the reference itself stops at 358 or 385 at N = 4096 depending on its BLAS (SURVEY.md
+    7.3); a sharded run changes the p'Ap grouping and may land on either."""
     k_ref, h_ref, x_ref = int(g[f"{blas}_k"]), g[f"{blas}_hist"], g[f"{blas}_x"]
-    assert abs(k - k_ref) <= 1, (label, k, k_ref)
+    k_refs = [k_ref] + ([int(g["naive_k"])] if any_provider_k and "naive_k" in g else [])
+    assert min(abs(k - kr) for kr in k_refs) <= 1, (label, k, k_refs)
     m = min(len(hist), len(h_ref))
     m_cmp = min(prefloor_length(h_ref), m)
     assert m_cmp >= min(m, 50), (label, m_cmp)

@@ -97,7 +97,9 @@ def test_two_gpu_solve_bitwise_vs_emulated_ranks(cgb, O, n, max_iter, exchange):
 
 @pytest.mark.parametrize("exchange", [0, 1], ids=["nccl", "fused"])
 def test_all_gpus_match_one_gpu_within_tolerance(cgb, O, golden_dir, exchange):
-    """G = every GPU on the box vs the reference golden run (k +-1, 1e-10 / 1e-9)."""
+    """G = every GPU on the box vs the reference golden run: residual norms 1e-10 before the
+    rounding floor, x 1e-9, iteration count within +-1 of one of the reference's own two
+    providers (358 OpenBLAS / 385 naive at N = 4096: the tail is order-dependent)."""
     from parity_util import check_against_reference
     G = _ngpu(cgb)
     if G < 2:
@@ -106,7 +108,7 @@ def test_all_gpus_match_one_gpu_within_tolerance(cgb, O, golden_dir, exchange):
     n = int(g["n"])
     res, nblk, b = _solve_sharded(cgb, O, n, G, n, exchange)
     for x, info, hist, nx, rr in res:
-        check_against_reference(info.k, hist, x, g, "openblas", "gen_n4096 G=%d" % G)
+        check_against_reference(info.k, hist, x, g, "openblas", "gen_n4096 G=%d" % G, any_provider_k=True)
     ref = O.solve(O.generate_lap2d(n), b, max_iter=n, nranks=G, nblk=nblk)
     assert res[0][1].k == ref.k and np.array_equal(res[0][2], ref.hist)
 
