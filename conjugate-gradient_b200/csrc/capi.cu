@@ -826,6 +826,7 @@ extern "C" int cgb_iterate(cgb_ctx *c, int64_t iters, float *ms)
     if (todo < 0) todo = 0;
     const bool profile = c->opt_profile != 0;
     const bool graph = c->opt_graph != 0 && !profile;
+    const bool lockstep = c->world > 1 && c->opt_exchange == 0;
     if (graph && !c->graph_exec && todo >= c->graph_unroll) {
         if ((rc = build_graph(c))) return rc;
     }
@@ -865,9 +866,14 @@ extern "C" int cgb_iterate(cgb_ctx *c, int64_t iters, float *ms)
             }
         }
         issued += batch;
-        // keep at most two batches in flight so the host never runs far ahead of the stop flag
+        // keep at most two batches in flight so the host never runs far ahead of the stop flag.
+        // ncclAllGather mode: the collectives of a batch run on every rank or on none, so all
+        // ranks must take the same stop decision -- wait for the batch just issued (the flag is
+        // then the same on every rank) instead of looking one batch back.  The fused exchange
+        // needs no such lockstep: launches after convergence communicate nothing.
         CK(cudaEventRecord(c->ev_batch[batch_idx & 1], c->stream));
-        if (batch_idx >= 1) CK(cudaEventSynchronize(c->ev_batch[(batch_idx - 1) & 1]));
+        if (lockstep) CK(cudaEventSynchronize(c->ev_batch[batch_idx & 1]));
+        else if (batch_idx >= 1) CK(cudaEventSynchronize(c->ev_batch[(batch_idx - 1) & 1]));
         ++batch_idx;
     }
     CK(cudaEventRecord(c->ev1, c->stream));

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "tune_gemv.jsonl"))
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--cases", default="40000:1,40000:8,20000:1,10000:1")
+    ap.add_argument("--only", default=None, help="comma-separated variant names (default: all)")
     args = ap.parse_args()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     peaks = {}
@@ -41,6 +42,8 @@ def main():
                            frac_of_measured_copy=gb / ms * 1e3 / peak)
                 print(json.dumps(rec)); out.write(json.dumps(rec) + "\n")
                 for v, name in enumerate(names):
+                    if args.only and name not in args.only.split(","):
+                        continue
                     try:
                         ms = ctx.bench_gemv(v, args.reps)
                     except cgb.CgbError as e:

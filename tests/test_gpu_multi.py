@@ -15,7 +15,7 @@ import threading
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(240)]   # a stuck collective must not eat GPU time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -36,11 +36,11 @@ def _run_ranks(G, fn):
         except BaseException as e:  # noqa: BLE001 - reported below
             err.append((r, e))
 
-    th = [threading.Thread(target=body, args=(r,)) for r in range(G)]
+    th = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(G)]
     for t in th:
         t.start()
     for t in th:
-        t.join(timeout=300)
+        t.join(timeout=120)
     assert not any(t.is_alive() for t in th), "a rank is stuck"
     if err:
         raise err[0][1]
