@@ -199,13 +199,18 @@ void CGSolver::solve(std::vector<double> &x)
 
 int gemv_variant_for(int NUM_THREADS, int BLOCK_WIDTH)
 {
-    // consumer warps per CTA from NUM_THREADS, column tile from BLOCK_WIDTH; the names are the
-    // ones cgb_gemv_variant_name() reports
-    const char *want;
-    if (BLOCK_WIDTH <= 256) want = (NUM_THREADS <= 288) ? "tma_w8r2c256s6" : "tma_w8r4c256s3";
-    else if (NUM_THREADS <= 160) want = "tma_w4r4c512s3";
-    else if (NUM_THREADS <= 288) want = "tma_w8r2c512s3";
-    else want = "tma_w16r1c512s3";
+    // NUM_THREADS -> consumer warps per CTA (4 / 8 / 16, + 1 producer warp);
+    // BLOCK_WIDTH -> column-tile width of the shared-memory ring (256 / 512 / 1024 doubles).
+    // Names are the ones cgb_gemv_variant_name() reports; all variants share one summation
+    // order, so the choice changes the launch shape and the speed, never the bits.
+    const int w = NUM_THREADS <= 128 ? 0 : NUM_THREADS <= 256 ? 1 : 2;
+    const int t = BLOCK_WIDTH <= 256 ? 0 : BLOCK_WIDTH <= 1024 ? 1 : 2;
+    static const char *const table[3][3] = {
+        {"tma_w4r4c256s6", "tma_w4r4c512s3", "tma_w4r2c1024s3"},
+        {"tma_w8r4c256s3", "tma_w8r2c512s3", "tma_w8r1c1024s3"},
+        {"tma_w16r2c256s3", "tma_w16r1c512s3", "tma_w16r1c512s3"},
+    };
+    const char *want = table[w][t];
     for (int v = 0; v < cgb_gemv_variant_count(); ++v)
         if (std::strcmp(cgb_gemv_variant_name(v), want) == 0) return v;
     return 0;
