@@ -110,7 +110,7 @@ struct cgb_ctx {
     int variant = 0, nblk = 0;
     long long slot = 0, slot_cap = 0;
     int opt_graph = 1, opt_profile = 0, opt_num_threads = 0, opt_block_width = 0, opt_transposed = 1;
-    int poll_every = 16, graph_unroll = 4;
+    int poll_every = 16, graph_unroll = 4, opt_pdl = 1;
 
     double *A = nullptr, *p = nullptr, *r = nullptr, *x = nullptr, *b = nullptr;
     double *apx = nullptr, *rrpart = nullptr, *scratch = nullptr, *hist = nullptr, *sink = nullptr;
@@ -191,6 +191,7 @@ GemvArgs make_gemv_args(const cgb_ctx *c, const double *v, int advance)
     a.nchunks = c->nchunks;
     a.hist = c->hist;
     a.advance = advance;
+    a.pdl = (advance && c->opt_pdl && !c->opt_profile) ? 1 : 0; // only inside the CG loop
     return a;
 }
 
@@ -210,6 +211,7 @@ VecArgs make_vec_args(const cgb_ctx *c)
     a.g = make_gather(c);
     a.n = c->n;
     a.tol = c->tol;
+    a.pdl = (c->opt_pdl && !c->opt_profile) ? 1 : 0;
     return a;
 }
 
@@ -710,6 +712,9 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
         if (value < 1 || value > 64) return fail(CGB_ERR_INVALID, "graph_unroll must be in [1, 64]");
         c->graph_unroll = (int)value;
         drop_graph(c);
+    } else if (k == "pdl") {
+        c->opt_pdl = value != 0;
+        drop_graph(c);
     } else if (k == "exchange") {
         if (value != 0 && value != 1) return fail(CGB_ERR_INVALID, "exchange must be 0 (nccl) or 1 (fused p2p)");
         if (c->world > 1 && value == 1 && !c->p2p_ready)
@@ -739,6 +744,7 @@ extern "C" int cgb_get_option(cgb_ctx *c, const char *key, int64_t *value)
     else if (k == "profile") *value = c->opt_profile;
     else if (k == "poll_every") *value = c->poll_every;
     else if (k == "graph_unroll") *value = c->graph_unroll;
+    else if (k == "pdl") *value = c->opt_pdl;
     else if (k == "exchange") *value = c->opt_exchange;
     else if (k == "num_threads") *value = c->opt_num_threads;
     else if (k == "block_width") *value = c->opt_block_width;

@@ -72,6 +72,7 @@ struct GemvArgs {
     long long nchunks;
     double *hist;         // nullable
     int advance;          // 1 inside the CG loop, 0 for the init / DEBUG mat-vecs
+    int pdl;              // host side: launch with the programmatic-dependent-launch attribute
 };
 
 // ------------------------------------------------------------------ reductions
@@ -204,6 +205,16 @@ __device__ __forceinline__ long long gather_index(const Gather &g, long long i)
     long long r = i / g.n_loc;
     if (r > g.world - 1) r = g.world - 1;
     return r * g.slot + (i - r * g.n_loc);
+}
+
+// ------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with the programmatic-stream-serialization attribute may become resident
+// before its predecessor has finished; everything it reads from the predecessor must come
+// after griddep_wait().  Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ mbarrier / TMA

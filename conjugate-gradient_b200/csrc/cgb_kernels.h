@@ -3,7 +3,32 @@
 
 #include "cgb_device.cuh"
 
+#include <cstring>
+
+#include <utility>
+
 namespace cgb {
+
+// Launch with (pdl = true) or without the programmatic-stream-serialization attribute: the
+// kernels of the CG loop are chained with programmatic dependent launches so that the next
+// kernel is already resident (and the mat-vec already prefetching A) when its predecessor ends.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem,
+                                 cudaStream_t stream, bool pdl, Args &&...args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- mat-vec (gemv.cu) --------------------------------------------------------------
 struct GemvVariant {
@@ -29,6 +54,7 @@ struct VecArgs {
     Gather g;
     long long n;
     double tol;
+    int pdl;                 // host side: chain update_xr / update_p with programmatic dependent launch
 };
 // r = b - A x0 ; p = r ; rrpart = chunk partials of r.p             (cg.cc:77-92)
 cudaError_t launch_init_residual(const VecArgs &a, cudaStream_t s);

@@ -68,16 +68,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
     uint64_t *empty = full + STAGES;
     double *qs = reinterpret_cast<double *>(empty + STAGES);      // [rows of this CTA]
 
-    if (a.st->done) return; // converged earlier: the whole launch is a no-op
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nblk = gridDim.x, c = blockIdx.x;
     const long long r0 = (long long)c * a.rows / nblk;
     const long long r1 = (long long)(c + 1) * a.rows / nblk;
     const int nrows = (int)(r1 - r0);
-    const unsigned tag = a.p2p ? exchange_tag(a.ctl) : 0u; // fused mode: tag + buffer of this exchange
-    const long long obase = a.slot_off;
-    const long long lbase = (long long)(tag & 1u) * a.bufstride + a.slot_off;
     const int nb = (nrows + TR - 1) / TR;          // row blocks, balanced below
     const int ntc = (int)((a.ld + TC - 1) / TC);   // column tiles
 
@@ -90,20 +85,26 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
     }
     __syncthreads();
 
+    // Programmatic dependent launch: this grid may become resident while the previous kernels of
+    // the iteration (update_xr / update_p, even the tail of the previous mat-vec) still run.
+    // A never changes, so the producer fills the whole ring with A tiles BEFORE waiting for
+    // them; only p, the scalars and the exchange tag are read after the wait.
+    griddep_launch_dependents();
+
     if (warp == CW) {
         // ===== producer: keeps the ring full, runs ahead across row blocks =====
         const uint64_t pol_a = l2_policy_evict_first();
         const uint64_t pol_p = l2_policy_evict_last();
-        unsigned it = 0;
-        for (int b = 0; b < nb; ++b) {
+        const unsigned total = (unsigned)nb * (unsigned)ntc;
+        // pipeline step `it` = (row block b, column tile t); part 1 = A rows, part 2 = p slice
+        auto issue = [&](unsigned it, bool partA, bool partP) {
+            const int b = (int)(it / (unsigned)ntc), t = (int)(it - (unsigned)b * (unsigned)ntc);
             const long long rb0 = r0 + (long long)b * nrows / nb;
             const int nr = (int)(r0 + (long long)(b + 1) * nrows / nb - rb0);
-            for (int t = 0; t < ntc; ++t, ++it) {
-                const int stage = it % STAGES;
-                const unsigned ph = (it / STAGES) & 1u;
-                const long long c0 = (long long)t * TC;
-                const int w = (int)((a.ld - c0 < TC) ? (a.ld - c0) : TC);
-                mbar_wait(&empty[stage], ph ^ 1u);
+            const int stage = it % STAGES;
+            const long long c0 = (long long)t * TC;
+            const int w = (int)((a.ld - c0 < TC) ? (a.ld - c0) : TC);
+            if (partA) {
                 if (lane == 0) mbar_arrive_expect_tx(&full[stage], (unsigned)((nr + 1) * w * 8));
                 __syncwarp();
                 double *dstA = sA + (size_t)stage * TR * TC;
@@ -115,12 +116,32 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
                         bulk_g2s_nohint(dstA + (size_t)j * TC, a.A + (rb0 + j) * a.ld + c0,
                                         (unsigned)(w * 8), &full[stage]);
                 }
-                if (lane == 31)
-                    bulk_g2s(sP + (size_t)stage * TC, a.v + c0, (unsigned)(w * 8), &full[stage], pol_p);
             }
+            if (partP && lane == 31)
+                bulk_g2s(sP + (size_t)stage * TC, a.v + c0, (unsigned)(w * 8), &full[stage], pol_p);
+        };
+        const unsigned npro = total < (unsigned)STAGES ? total : (unsigned)STAGES;
+        for (unsigned it = 0; it < npro; ++it) issue(it, true, false);   // A only: no dependency
+        griddep_wait();                                                    // p is final from here on
+        const int done = a.st->done;
+        for (unsigned it = 0; it < npro; ++it) issue(it, false, true);
+        if (done) {
+            // converged earlier: the launch is a no-op, but the copies in flight must land
+            // before the CTA may exit
+            for (unsigned it = 0; it < npro; ++it) mbar_wait(&full[it % STAGES], 0u);
+            return;
+        }
+        for (unsigned it = npro; it < total; ++it) {
+            mbar_wait(&empty[it % STAGES], ((it / STAGES) & 1u) ^ 1u);
+            issue(it, true, true);
         }
     } else {
         // ===== consumers =====
+        griddep_wait();
+        if (a.st->done) return; // converged earlier: the whole launch is a no-op
+        const unsigned tag = a.p2p ? exchange_tag(a.ctl) : 0u; // fused mode: tag + buffer of this exchange
+        const long long obase = a.slot_off;
+        const long long lbase = (long long)(tag & 1u) * a.bufstride + a.slot_off;
         if (a.advance && c == 0 && warp == 0) advance_state(a, lane);
         unsigned it = 0;
         for (int b = 0; b < nb; ++b) {
@@ -200,6 +221,8 @@ __global__ void __launch_bounds__(W * 32) gemv_ldg_kernel(const GemvArgs a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *qs = reinterpret_cast<double *>(smem_raw);
 
+    griddep_launch_dependents();
+    griddep_wait();
     if (a.st->done) return;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -306,8 +329,7 @@ cudaError_t tma_launch(const GemvArgs &a, int nblk, cudaStream_t s)
     auto k = gemv_tma_kernel<CW, RPW, TC, STAGES, MINB, POL>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<nblk, (CW + 1) * 32, smem, s>>>(a);
-    return cudaGetLastError();
+    return launch_kernel(k, nblk, (CW + 1) * 32, smem, s, a.pdl != 0, a);
 }
 
 template <int W, int RPW, int UNR>
@@ -320,8 +342,7 @@ cudaError_t ldg_launch(const GemvArgs &a, int nblk, cudaStream_t s)
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k<<<nblk, W * 32, smem, s>>>(a);
-    return cudaGetLastError();
+    return launch_kernel(k, nblk, W * 32, smem, s, a.pdl != 0, a);
 }
 
 const GemvVariant kVariants[] = {

@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a)
     extern __shared__ double sh_part[]; // world * nblk block partials
     __shared__ double wsum[8];
     __shared__ double sh_alpha;
+    griddep_launch_dependents(); // let update_p (and, behind it, the next mat-vec) become resident
+    griddep_wait();              // ... but read nothing before the mat-vec has completed
     if (a.st->done) return;
     const int tid = threadIdx.x;
     // fused exchange: every read below polls its own LL entry until the owning rank's mat-vec
@@ -99,6 +101,8 @@ __global__ void __launch_bounds__(kChunk) update_p_kernel(const VecArgs a, long 
     __shared__ double sh_bcast;
     __shared__ int sh_done;
     const int tid = threadIdx.x;
+    griddep_launch_dependents(); // the next mat-vec may start prefetching A now
+    griddep_wait();              // update_xr has completed: rrpart and r are final
     // block 0 may raise `done` while this launch is still running: sample it once per block
     if (tid == 0) sh_done = a.st->done;
     __syncthreads();
@@ -274,15 +278,14 @@ cudaError_t launch_init_residual(const VecArgs &a, cudaStream_t s)
 cudaError_t launch_update_xr(const VecArgs &a, cudaStream_t s)
 {
     const size_t smem = (size_t)a.g.world * a.g.nblk * sizeof(double);
-    update_xr_kernel<<<grid_for(a.n), kChunk, smem, s>>>(a);
-    return cudaGetLastError();
+    return launch_kernel(update_xr_kernel, grid_for(a.n), kChunk, smem, s, a.pdl != 0, a);
 }
 
 cudaError_t launch_update_p(const VecArgs &a, cudaStream_t s)
 {
     const long long nchunks = grid_for(a.n);
-    update_p_kernel<<<(int)nchunks, kChunk, (size_t)nchunks * sizeof(double), s>>>(a, nchunks);
-    return cudaGetLastError();
+    return launch_kernel(update_p_kernel, (int)nchunks, kChunk, (size_t)nchunks * sizeof(double), s,
+                         a.pdl != 0, a, nchunks);
 }
 
 cudaError_t launch_finalize(const VecArgs &a, cudaStream_t s)

@@ -111,6 +111,8 @@ int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
  * "num_threads"/"block_width": the NUM_THREADS / BLOCK_WIDTH command-line knobs of the
  * reference CUDA program (code/CUDA/cg_main.cc:21-25), mapped onto threads per CTA and
  * column-tile width of the mat-vec; "graph": 0/1 CUDA-graph replay of the iteration;
+ * "pdl": 0/1 programmatic dependent launch between the kernels of the iteration (the next
+ * mat-vec prefetches A while the vector updates still run);
  * "exchange": 0 ncclAllGather / 1 fused peer stores (see cgb_exchange_import);
  * "transposed": the reference's true/false kernel switch (accepted, A is symmetric). */
 int cgb_set_option(cgb_ctx *ctx, const char *key, int64_t value);
