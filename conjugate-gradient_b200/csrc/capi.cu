@@ -110,7 +110,7 @@ struct cgb_ctx {
     int variant = 0, nblk = 0;
     long long slot = 0, slot_cap = 0;
     int opt_graph = 1, opt_profile = 0, opt_num_threads = 0, opt_block_width = 0, opt_transposed = 1;
-    int poll_every = 16, graph_unroll = 4, opt_pdl = 1;
+    int poll_every = 16, graph_unroll = 16, opt_pdl = 1;
 
     double *A = nullptr, *p = nullptr, *r = nullptr, *x = nullptr, *b = nullptr;
     double *apx = nullptr, *rrpart = nullptr, *scratch = nullptr, *hist = nullptr, *sink = nullptr;
