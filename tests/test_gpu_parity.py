@@ -238,3 +238,34 @@ def test_solve_matches_reference_golden(cgb, O, golden_dir, tmp_path):
         x, info, hist, nx, rr, _ = _solve_gpu(cgb, n, setup, max_iter)
         check_against_reference(info.k, hist, x, g, "openblas", os.path.basename(f))
         assert abs(nx - float(g["openblas_norm_x"])) <= 1e-6 * nx
+
+
+# --------------------------------------------------------------------------- beyond the reference
+def test_n_beyond_int32_indexing(cgb, O):
+    """N = 46400 > 46340: the reference's `int` index i*m_n+j overflows (matrix.hh:17,
+    cg.cc:80), so there is no reference run -- size-independent properties
+    instead: A.1 = analytic row sums, A e_j = generator row j (symmetry) at both ends of the
+    index range, and the recursive residual of 40 CG iterations equals the true residual
+    ||A x - b|| recomputed by the DEBUG block."""
+    n = 46400
+    inc = int(np.floor(np.sqrt(n)))
+    with _ctx(cgb, n) as ctx:
+        ctx.generate_lap2d()
+        y, _ = ctx.gemv(np.ones(n))
+        i = np.arange(n)
+        neigh = (i > 0).astype(float) + (i < n - 1) + (i > inc) + (i < n - 1 - inc)
+        assert np.array_equal(y, 4.0 - neigh)
+        for j in (0, inc, inc + 1, n // 2, n - 2 - inc, n - 1):
+            e = np.zeros(n)
+            e[j] = 1.0
+            yj, _ = ctx.gemv(e)
+            assert np.array_equal(yj, O.generate_lap2d_rows(n, j, 1)[0]), j
+        b = cgb.init_source_term(n)
+        ctx.set_rhs(b)
+        x = np.zeros(n)
+        info, hist = ctx.solve(x, max_iter=40, tol=1e-10, history=True)
+        nx, rr = ctx.residual_check()
+    assert info.k == 40 and len(hist) == 40 and np.all(np.diff(np.sqrt(hist[5:])) != 0)
+    true_resid = rr * np.linalg.norm(b)
+    assert abs(true_resid - np.sqrt(info.rsold)) <= 1e-9 * true_resid
+    assert abs(nx - np.linalg.norm(x)) <= 1e-12 * nx
