@@ -82,19 +82,22 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------ reference arm
-def ref_binary():
-    return os.path.join(ROOT, "oracle", "_ref", "cgsolver_ref")
+def ref_binary(ranks: int = 1):
+    return os.path.join(ROOT, "oracle", "_ref", "cgsolver_ref" if ranks == 1 else "cgsolver_ref_mp")
 
 
-def run_reference_cpu(n: int, iters: int, threads: int, skip: int = 0):
-    """Runs the unmodified reference MPI solver (1 rank, OpenBLAS with `threads` threads) for
-    `iters` iterations and returns steady-state numbers from its dgemv timestamps."""
-    exe = ref_binary()
+def run_reference_cpu(n: int, iters: int, threads: int, skip: int = 0, ranks: int = 1):
+    """Runs the unmodified reference MPI solver for `iters` iterations and returns steady-state
+    numbers from rank 0's dgemv timestamps.  ranks == 1: one rank, OpenBLAS with `threads`
+    threads.  ranks > 1: `ranks` MPI ranks forked on this host (oracle/ref_shim/mpi_fork.cc),
+    threads // ranks OpenBLAS threads each; every rank holds the full matrix, as in the reference."""
+    exe = ref_binary(ranks)
     if not os.path.exists(exe):
         raise FileNotFoundError(exe + " (built by oracle/Makefile from /root/reference)")
     with tempfile.TemporaryDirectory() as td:
+        per = max(1, threads // ranks)
         env = dict(os.environ, CGREF_BLAS="auto", CGREF_GEMV_TIMES=os.path.join(td, "t"),
-                   OPENBLAS_NUM_THREADS=str(threads), OMP_NUM_THREADS=str(threads))
+                   CGREF_NP=str(ranks), OPENBLAS_NUM_THREADS=str(per), OMP_NUM_THREADS=str(per))
         t0 = time.time()
         res = subprocess.run([exe, str(n), os.path.join(td, "results.txt"), str(iters)], env=env,
                              capture_output=True, text=True)
@@ -125,13 +128,14 @@ def reference_arm(args):
     per_step = max(1, min(5, 60 // max(1, args.steps + args.warmup)))
     total = per_step * (args.steps + args.warmup)
     try:
-        r = run_reference_cpu(n, total, cores, skip=per_step * args.warmup)
+        r = run_reference_cpu(n, total, cores, skip=per_step * args.warmup, ranks=args.cpu_ranks)
     except Exception as e:  # the oracle always exists in a built tree; say why if it does not
         print(json.dumps({"impl": "reference", "unavailable": str(e)[:200]}))
         return 0
-    sample = ("unmodified reference code/MPI solver, 1 rank, %s; N=%d; %d iterations per step "
-              "(of %d), %d warm-up + %d timed steps in one process; steady-state loop time from "
-              "dgemv timestamps" % (r["blas"], n, per_step, ITERS_PER_STEP, args.warmup, args.steps))
+    sample = ("unmodified reference code/MPI solver, %d rank(s), %s; N=%d; %d iterations per step "
+              "(of %d), %d warm-up + %d timed steps in one run; steady-state loop time from "
+              "dgemv timestamps" % (args.cpu_ranks, r["blas"], n, per_step, ITERS_PER_STEP, args.warmup,
+                                    args.steps))
     value = r["it_per_s"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -372,13 +376,14 @@ def product_arm(args):
         cores = os.cpu_count() or 1
         sample_iters = args.cpu_iters
         try:
-            r = run_reference_cpu(n, sample_iters, cores)
+            r = run_reference_cpu(n, sample_iters, cores, ranks=args.cpu_ranks)
             cpu_baseline = {
                 "value": r["it_per_s"], "unit": UNIT, "cores": cores, "kind": "reference",
-                "sample": ("unmodified reference code/MPI solver (oracle/_ref/cgsolver_ref), 1 rank, %s, "
+                "sample": ("unmodified reference code/MPI solver (oracle/_ref), %d rank(s), %s, "
                            "N=%d, %d of the %d iterations; steady-state loop time from dgemv timestamps "
                            "(%.2f s loop, %.1f s process incl. its -O0 matrix generation)"
-                           % (r["blas"], n, r["iters"], iters, r["loop_seconds"], r["wall_seconds"])),
+                           % (args.cpu_ranks, r["blas"], n, r["iters"], iters, r["loop_seconds"],
+                              r["wall_seconds"])),
                 "gemv_gbs": 8.0 * n * n * r["it_per_s"] / 1e9,
             }
         except Exception as e:
@@ -429,6 +434,8 @@ def main():
     ap.add_argument("--poll-every", dest="poll_every", type=int, default=None)
     ap.add_argument("--exchange", type=int, default=None)
     ap.add_argument("--cpu-iters", dest="cpu_iters", type=int, default=40)
+    ap.add_argument("--cpu-ranks", dest="cpu_ranks", type=int, default=1,
+                    help="MPI ranks of the CPU reference (forked on this host; default 1 rank x all threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

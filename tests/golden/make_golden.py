@@ -5,9 +5,11 @@ The reference ships no tests or golden vectors, so the pin
 outputs of its own unmodified sources (/root/reference/code/MPI/*.cc, compiled by
 oracle/Makefile into oracle/_ref/ against the stand-in mpi.h/cblas.h) with a real
 OpenBLAS 0.3.15 behind cblas_* ("openblas") and with plain left-to-right loops ("naive").
-Run from the repo root:   python tests/golden/make_golden.py [--full]
+Run from the repo root:   python tests/golden/make_golden.py [--full | --ranks]
 (--full adds BASELINE.json's full-size configs: N=20000 to convergence and N=40000 x 200
 iterations, OpenBLAS provider only; ~2 minutes and 13 GB of host memory.)
+(--ranks adds multi-rank runs of the reference: P = 2, 4, 8 ranks forked on this host by
+oracle/ref_shim/mpi_fork.cc -- the reference's own iteration count depends on P.)
 Needs /root/reference (to build oracle/_ref); the produced fixtures are committed so the
 tests never need it.
 
@@ -52,6 +54,27 @@ def run_ref(args, blas, tail=(), threads=8):
                 results_row=row)
 
 
+def run_ref_ranks(n, ranks, max_iter=None, threads=8):
+    """The reference at `ranks` MPI ranks (fork shim); history = the all-reduced r'r values."""
+    exe = os.path.join(REF, "cgsolver_ref_mp")
+    with tempfile.TemporaryDirectory() as td:
+        per = max(1, threads // ranks)
+        env = dict(os.environ, CGREF_BLAS="openblas", CGREF_NP=str(ranks),
+                   CGREF_ALLREDUCE=os.path.join(td, "ar"), CGREF_XOUT=os.path.join(td, "x"),
+                   OPENBLAS_NUM_THREADS=str(per), OMP_NUM_THREADS=str(per))
+        args = [exe, str(n), os.path.join(td, "results.txt")] + ([] if max_iter is None else [str(max_iter)])
+        res = subprocess.run(args, env=env, check=True, capture_output=True, text=True)
+        m = LINE.search(res.stdout)
+        assert m, res.stdout
+        ar = np.fromfile(os.path.join(td, "ar"), dtype=np.float64)
+        x = np.fromfile(os.path.join(td, "x"), dtype=np.float64)
+        row = open(os.path.join(td, "results.txt")).read().strip()
+    # ar = [r.p, (p'Ap, r'r) per executed iteration]
+    return dict(k=int(m.group(1)), resid_print=float(m.group(2)), norm_x=float(m.group(3)),
+                rel_resid=float(m.group(4)), hist=ar[2::2].copy(), x=x, stdout_line=m.group(0),
+                results_row=row)
+
+
 def save(name, meta, runs):
     d = dict(meta)
     for blas, r in runs.items():
@@ -67,6 +90,11 @@ def main():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
     gen = os.path.join(REF, "cgsolver_ref")
     mtx = os.path.join(REF, "cgsolver_ref_mtx")
+    if "--ranks" in sys.argv:
+        for n, ranks in [(4096, 2), (4096, 4), (4096, 8), (2048, 2), (1000, 3)]:
+            runs = {"openblas": run_ref_ranks(n, ranks)}
+            save(f"ranks_n{n}_p{ranks}", dict(n=n, max_iter=n, kind="generate_lap2d", ranks=ranks), runs)
+        return
     if "--full" in sys.argv:
         for n, max_iter in [(20000, None), (40000, 200)]:
             tail = [] if max_iter is None else [str(max_iter)]

@@ -221,6 +221,8 @@ def test_solve_matches_reference_golden(cgb, O, golden_dir, tmp_path):
     assert cases, "golden fixtures missing"
     for f in cases:
         g = np.load(f)
+        if "ranks" in g:
+            continue  # multi-rank runs of the reference: tests/test_gpu_multi.py
         n, max_iter = int(g["n"]), int(g["max_iter"])
         b = O.init_source_term(n)
         if str(g["kind"]) == "mtx":

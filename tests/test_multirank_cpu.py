@@ -69,3 +69,38 @@ def test_product_arm_refuses_to_run_without_gpu():
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_reference_forked_ranks_match_oracle_emulated_ranks(O, tmp_path):
+    """The UNMODIFIED reference at P = 1, 2, 3 forked MPI ranks (oracle/_ref/cgsolver_ref_mp,
+    ref_shim/mpi_fork.cc) against the oracle's emulated ranks: same partition rule (N = 1001
+    leaves a remainder on the last rank), all-reduced r'r history within 1e-10 before the
+    rounding floor, gathered x within 1e-9."""
+    import pytest
+    from parity_util import prefloor_length
+    exe = os.path.join(ROOT, "oracle", "_ref", "cgsolver_ref_mp")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/cgsolver_ref_mp not built (needs /root/reference once)")
+    n = 1001
+    A, b = O.generate_lap2d(n), O.init_source_term(n)
+    ks = []
+    for P in (1, 2, 3):
+        ar, xo, res = tmp_path / ("ar%d" % P), tmp_path / ("x%d" % P), tmp_path / "res.txt"
+        env = dict(os.environ, CGREF_NP=str(P), CGREF_BLAS="naive", OMP_NUM_THREADS="2",
+                   CGREF_ALLREDUCE=str(ar), CGREF_XOUT=str(xo))
+        r = subprocess.run([exe, str(n), str(res)], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-800:]
+        hist = np.fromfile(str(ar))[2::2]
+        x = np.fromfile(str(xo))
+        assert len(x) == n
+        k = int(r.stdout.split("[STEP ")[1].split("]")[0])
+        ks.append(k)
+        assert len(hist) == k + 1                       # converged: the breaking iteration is logged
+        o = O.solve(A, b, nranks=P, nblk=148)
+        m = min(prefloor_length(hist), len(o.hist))
+        rel = np.abs(np.sqrt(o.hist[:m]) - np.sqrt(hist[:m])) / np.sqrt(hist[:m])
+        assert m >= 50 and rel.max() <= 1e-10, (P, float(rel.max()))
+        assert np.linalg.norm(o.x - x) <= 1e-9 * np.linalg.norm(x), P
+        assert abs(o.k - k) <= 5                        # order-dependent tail (SURVEY.md 7.3)
+    rows = (tmp_path / "res.txt").read_text().splitlines()
+    assert [row.split(",")[:2] for row in rows] == [[str(n), "1"], [str(n), "2"], [str(n), "3"]]
