@@ -101,6 +101,6 @@ def test_reference_forked_ranks_match_oracle_emulated_ranks(O, tmp_path):
         rel = np.abs(np.sqrt(o.hist[:m]) - np.sqrt(hist[:m])) / np.sqrt(hist[:m])
         assert m >= 50 and rel.max() <= 1e-10, (P, float(rel.max()))
         assert np.linalg.norm(o.x - x) <= 1e-9 * np.linalg.norm(x), P
-        assert abs(o.k - k) <= 5                        # order-dependent tail
+        assert abs(o.k - k) <= 0.1 * k                  # order-dependent tail (up to ~5 %)
     rows = (tmp_path / "res.txt").read_text().splitlines()
     assert [row.split(",")[:2] for row in rows] == [[str(n), "1"], [str(n), "2"], [str(n), "3"]]
