@@ -432,6 +432,8 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
     CKB(cudaMemsetAsync(c->rrpart, 0, (size_t)c->nchunks * sizeof(double), c->stream));
     CKB(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
     CKB(cudaStreamSynchronize(c->stream));
+    CKB(preload_vec_kernels());
+    CKB(gemv_variant(c->variant).preload());
 #undef CKB
     *out = c;
     return CGB_OK;
@@ -701,6 +703,7 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
             return fail(CGB_ERR_INVALID, "gemv_variant %lld out of range", (long long)value);
         set_variant(c, (int)value);
         drop_graph(c);
+        if (use_device(c) == CGB_OK) gemv_variant(c->variant).preload();
     } else if (k == "graph") {
         c->opt_graph = value != 0;
     } else if (k == "profile") {

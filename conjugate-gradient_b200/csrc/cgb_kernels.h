@@ -36,6 +36,7 @@ struct GemvVariant {
     int ctas_per_sm; // grid = sm_count * ctas_per_sm persistent CTAs (= p'Ap block partials)
     int threads;
     cudaError_t (*launch)(const GemvArgs &a, int nblk, cudaStream_t s);
+    cudaError_t (*preload)(); // load the kernel now (lazy module loading), not at its first launch
 };
 int gemv_variant_count();
 const GemvVariant &gemv_variant(int i);
@@ -43,6 +44,8 @@ cudaError_t launch_read_stream(const double *A, long long ndoubles, double *sink
                                cudaStream_t s);
 
 // ---- vector kernels (vec.cu) -------------------------------------------------------
+// load every kernel of the solve path now instead of at first launch
+cudaError_t preload_vec_kernels();
 struct VecArgs {
     double *x, *r, *p;       // full-length (ld) replicated work vectors
     const double *b;

@@ -332,6 +332,21 @@ cudaError_t tma_launch(const GemvArgs &a, int nblk, cudaStream_t s)
     return launch_kernel(k, nblk, (CW + 1) * 32, smem, s, a.pdl != 0, a);
 }
 
+// Lazy module loading would otherwise load the kernel at its first launch -- inside the caller's
+// timed solve(); querying its attributes loads it at context creation instead.
+template <int CW, int RPW, int TC, int STAGES, int MINB, int POL = 0>
+cudaError_t tma_preload()
+{
+    cudaFuncAttributes fa;
+    return cudaFuncGetAttributes(&fa, gemv_tma_kernel<CW, RPW, TC, STAGES, MINB, POL>);
+}
+template <int W, int RPW, int UNR>
+cudaError_t ldg_preload()
+{
+    cudaFuncAttributes fa;
+    return cudaFuncGetAttributes(&fa, gemv_ldg_kernel<W, RPW, UNR>);
+}
+
 template <int W, int RPW, int UNR>
 cudaError_t ldg_launch(const GemvArgs &a, int nblk, cudaStream_t s)
 {
@@ -347,23 +362,23 @@ cudaError_t ldg_launch(const GemvArgs &a, int nblk, cudaStream_t s)
 
 const GemvVariant kVariants[] = {
     // name               ctas/SM  threads  launcher
-    {"tma_w8r2c512s3", 1, 288, tma_launch<8, 2, 512, 3, 1>},
-    {"tma_w8r1c512s6", 1, 288, tma_launch<8, 1, 512, 6, 1>},
-    {"tma_w4r4c512s3", 1, 160, tma_launch<4, 4, 512, 3, 1>},
-    {"tma_w8r2c256s6", 1, 288, tma_launch<8, 2, 256, 6, 1>},
-    {"tma_w8r4c256s3", 1, 288, tma_launch<8, 4, 256, 3, 1>},
-    {"tma_w16r1c512s3", 1, 544, tma_launch<16, 1, 512, 3, 1>},
-    {"tma2_w4r2c512s3", 2, 160, tma_launch<4, 2, 512, 3, 2>},
-    {"tma2_w8r1c256s6", 2, 288, tma_launch<8, 1, 256, 6, 2>},
-    {"tma_w4r4c256s6", 1, 160, tma_launch<4, 4, 256, 6, 1>},
-    {"tma_w8r1c1024s3", 1, 288, tma_launch<8, 1, 1024, 3, 1>},
-    {"tma_w4r2c1024s3", 1, 160, tma_launch<4, 2, 1024, 3, 1>},
-    {"tma_w16r2c256s3", 1, 544, tma_launch<16, 2, 256, 3, 1>},
-    {"tma2_w4r1c1024s3", 2, 160, tma_launch<4, 1, 1024, 3, 2>},
-    {"tma_w8r2c512s3_nohint", 1, 288, tma_launch<8, 2, 512, 3, 1, 1>},
-    {"ldg_w8r4u2", 4, 256, ldg_launch<8, 4, 2>},
-    {"ldg_w8r2u4", 4, 256, ldg_launch<8, 2, 4>},
-    {"ldg_w16r4u2", 2, 512, ldg_launch<16, 4, 2>},
+    {"tma_w8r2c512s3", 1, 288, tma_launch<8, 2, 512, 3, 1>, tma_preload<8, 2, 512, 3, 1>},
+    {"tma_w8r1c512s6", 1, 288, tma_launch<8, 1, 512, 6, 1>, tma_preload<8, 1, 512, 6, 1>},
+    {"tma_w4r4c512s3", 1, 160, tma_launch<4, 4, 512, 3, 1>, tma_preload<4, 4, 512, 3, 1>},
+    {"tma_w8r2c256s6", 1, 288, tma_launch<8, 2, 256, 6, 1>, tma_preload<8, 2, 256, 6, 1>},
+    {"tma_w8r4c256s3", 1, 288, tma_launch<8, 4, 256, 3, 1>, tma_preload<8, 4, 256, 3, 1>},
+    {"tma_w16r1c512s3", 1, 544, tma_launch<16, 1, 512, 3, 1>, tma_preload<16, 1, 512, 3, 1>},
+    {"tma2_w4r2c512s3", 2, 160, tma_launch<4, 2, 512, 3, 2>, tma_preload<4, 2, 512, 3, 2>},
+    {"tma2_w8r1c256s6", 2, 288, tma_launch<8, 1, 256, 6, 2>, tma_preload<8, 1, 256, 6, 2>},
+    {"tma_w4r4c256s6", 1, 160, tma_launch<4, 4, 256, 6, 1>, tma_preload<4, 4, 256, 6, 1>},
+    {"tma_w8r1c1024s3", 1, 288, tma_launch<8, 1, 1024, 3, 1>, tma_preload<8, 1, 1024, 3, 1>},
+    {"tma_w4r2c1024s3", 1, 160, tma_launch<4, 2, 1024, 3, 1>, tma_preload<4, 2, 1024, 3, 1>},
+    {"tma_w16r2c256s3", 1, 544, tma_launch<16, 2, 256, 3, 1>, tma_preload<16, 2, 256, 3, 1>},
+    {"tma2_w4r1c1024s3", 2, 160, tma_launch<4, 1, 1024, 3, 2>, tma_preload<4, 1, 1024, 3, 2>},
+    {"tma_w8r2c512s3_nohint", 1, 288, tma_launch<8, 2, 512, 3, 1, 1>, tma_preload<8, 2, 512, 3, 1, 1>},
+    {"ldg_w8r4u2", 4, 256, ldg_launch<8, 4, 2>, ldg_preload<8, 4, 2>},
+    {"ldg_w8r2u4", 4, 256, ldg_launch<8, 2, 4>, ldg_preload<8, 2, 4>},
+    {"ldg_w16r4u2", 2, 512, ldg_launch<16, 4, 2>, ldg_preload<16, 4, 2>},
 };
 
 } // namespace

@@ -269,6 +269,19 @@ inline int grid_for(long long n) { return (int)((n + kChunk - 1) / kChunk); }
 
 } // namespace
 
+cudaError_t preload_vec_kernels()
+{
+    cudaFuncAttributes fa;
+    cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&fa, init_residual_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, update_xr_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, update_p_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, finalize_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, debug_partials_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, debug_final_kernel)) != cudaSuccess) return e;
+    return cudaFuncGetAttributes(&fa, exchange_collect_kernel);
+}
+
 cudaError_t launch_init_residual(const VecArgs &a, cudaStream_t s)
 {
     init_residual_kernel<<<grid_for(a.n), kChunk, 0, s>>>(a);
