@@ -370,7 +370,7 @@ const GemvVariant kVariants[] = {
     {"tma_w16r1c512s3", 1, 544, tma_launch<16, 1, 512, 3, 1>, tma_preload<16, 1, 512, 3, 1>},
     {"tma2_w4r2c512s3", 2, 160, tma_launch<4, 2, 512, 3, 2>, tma_preload<4, 2, 512, 3, 2>},
     {"tma2_w8r1c256s6", 2, 288, tma_launch<8, 1, 256, 6, 2>, tma_preload<8, 1, 256, 6, 2>},
-    {"tma_w4r4c256s6", 1, 160, tma_launch<4, 4, 256, 6, 1>, tma_preload<4, 4, 256, 6, 1>},
+    {"tma_w4r8c256s3", 1, 160, tma_launch<4, 8, 256, 3, 1>, tma_preload<4, 8, 256, 3, 1>},
     {"tma_w8r1c1024s3", 1, 288, tma_launch<8, 1, 1024, 3, 1>, tma_preload<8, 1, 1024, 3, 1>},
     {"tma_w4r2c1024s3", 1, 160, tma_launch<4, 2, 1024, 3, 1>, tma_preload<4, 2, 1024, 3, 1>},
     {"tma_w16r2c256s3", 1, 544, tma_launch<16, 2, 256, 3, 1>, tma_preload<16, 2, 256, 3, 1>},

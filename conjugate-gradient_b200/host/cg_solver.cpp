@@ -206,7 +206,7 @@ int gemv_variant_for(int NUM_THREADS, int BLOCK_WIDTH)
     const int w = NUM_THREADS <= 128 ? 0 : NUM_THREADS <= 256 ? 1 : 2;
     const int t = BLOCK_WIDTH <= 256 ? 0 : BLOCK_WIDTH <= 1024 ? 1 : 2;
     static const char *const table[3][3] = {
-        {"tma_w4r4c256s6", "tma_w4r4c512s3", "tma_w4r2c1024s3"},
+        {"tma_w4r8c256s3", "tma_w4r4c512s3", "tma_w4r2c1024s3"},
         {"tma_w8r4c256s3", "tma_w8r2c512s3", "tma_w8r1c1024s3"},
         {"tma_w16r2c256s3", "tma_w16r1c512s3", "tma_w16r1c512s3"},
     };
