@@ -110,6 +110,9 @@ struct cgb_ctx {
     int variant = 0, nblk = 0;
     long long slot = 0, slot_cap = 0;
     int opt_graph = 1, opt_profile = 0, opt_num_threads = 0, opt_block_width = 0, opt_transposed = 1;
+    int opt_compat = 0;            // 1: the reference's mat-vec topologies (compat.cu)
+    double *compat_part = nullptr; // chunk partials of the compat mat-vec
+    size_t compat_part_cap = 0;
     int poll_every = 16, graph_unroll = 16, opt_pdl = 1;
 
     double *A = nullptr, *p = nullptr, *r = nullptr, *x = nullptr, *b = nullptr;
@@ -233,6 +236,14 @@ void drop_graph(cgb_ctx *c)
 // the mat-vec and, for world > 1, the gather of its result
 int launch_matvec(cgb_ctx *c, const double *v, int advance, int variant)
 {
+    if (c->opt_compat) { // reference topologies, NUM_THREADS / BLOCK_WIDTH literal (single GPU)
+        GemvArgs a = make_gemv_args(c, v, advance);
+        a.pdl = 0;
+        CK(launch_compat_matvec(a, c->nblk, c->opt_num_threads, c->opt_block_width, c->opt_transposed,
+                                c->compat_part, c->stream));
+        c->kernel_launches += 2;
+        return CGB_OK;
+    }
     const GemvArgs a = make_gemv_args(c, v, advance);
     CK(gemv_variant(variant).launch(a, c->sm_count * gemv_variant(variant).ctas_per_sm, c->stream));
     c->kernel_launches += 1;
@@ -453,6 +464,7 @@ extern "C" int cgb_destroy(cgb_ctx *c)
     for (double *p : bufs)
         if (p) cudaFree(p);
     if (c->st) cudaFree(c->st);
+    if (c->compat_part) cudaFree(c->compat_part);
     if (c->ll) cudaFree(c->ll);
     if (c->ctl) cudaFree(c->ctl);
     if (c->h_done) cudaFreeHost(c->h_done);
@@ -715,6 +727,27 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
         if (value < 1 || value > 64) return fail(CGB_ERR_INVALID, "graph_unroll must be in [1, 64]");
         c->graph_unroll = (int)value;
         drop_graph(c);
+    } else if (k == "compat") {
+        if (value != 0) {
+            if (c->world != 1) return fail(CGB_ERR_INVALID, "compat mat-vec is single-GPU (like the reference CUDA program)");
+            if (c->opt_num_threads < 1 || c->opt_num_threads > 1024 || c->opt_block_width < 1)
+                return fail(CGB_ERR_INVALID, "compat needs num_threads in [1, 1024] and block_width >= 1 set first");
+            int rc = use_device(c);
+            if (rc) return rc;
+            const size_t need = compat_part_doubles(c->n, c->opt_block_width);
+            if (need > c->compat_part_cap) {
+                if (c->compat_part) cudaFree(c->compat_part);
+                c->compat_part = nullptr;
+                c->compat_part_cap = 0;
+                cudaError_t e = cudaMalloc(&c->compat_part, need * sizeof(double));
+                if (e != cudaSuccess)
+                    return fail(CGB_ERR_NOMEM, "compat partial buffer (%zu MB): %s", need * 8 >> 20,
+                                cudaGetErrorString(e));
+                c->compat_part_cap = need;
+            }
+        }
+        c->opt_compat = value != 0;
+        drop_graph(c);
     } else if (k == "pdl") {
         c->opt_pdl = value != 0;
         drop_graph(c);
@@ -728,10 +761,15 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
         drop_graph(c);
     } else if (k == "num_threads") {
         c->opt_num_threads = (int)value;
+        c->opt_compat = 0; // re-enable with "compat" = 1 (re-validates, re-sizes the partial buffer)
+        drop_graph(c);
     } else if (k == "block_width") {
         c->opt_block_width = (int)value;
+        c->opt_compat = 0;
+        drop_graph(c);
     } else if (k == "transposed") {
         c->opt_transposed = value != 0;
+        drop_graph(c);
     } else {
         return fail(CGB_ERR_INVALID, "unknown option '%s'", key);
     }
@@ -747,6 +785,7 @@ extern "C" int cgb_get_option(cgb_ctx *c, const char *key, int64_t *value)
     else if (k == "profile") *value = c->opt_profile;
     else if (k == "poll_every") *value = c->poll_every;
     else if (k == "graph_unroll") *value = c->graph_unroll;
+    else if (k == "compat") *value = c->opt_compat;
     else if (k == "pdl") *value = c->opt_pdl;
     else if (k == "exchange") *value = c->opt_exchange;
     else if (k == "num_threads") *value = c->opt_num_threads;
@@ -856,7 +895,7 @@ extern "C" int cgb_iterate(cgb_ctx *c, int64_t iters, float *ms)
         while (i < batch) {
             if (graph && c->graph_exec && batch - i >= c->graph_unroll) {
                 CK(cudaGraphLaunch(c->graph_exec, c->stream));
-                c->kernel_launches += 3LL * c->graph_unroll;
+                c->kernel_launches += (c->opt_compat ? 4LL : 3LL) * c->graph_unroll;
                 i += c->graph_unroll;
             } else if (profile) {
                 const long long slot = 2 * (issued + i);

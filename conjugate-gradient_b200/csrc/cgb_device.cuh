@@ -207,6 +207,21 @@ __device__ __forceinline__ long long gather_index(const Gather &g, long long i)
     return r * g.slot + (i - r * g.n_loc);
 }
 
+// Called by one full warp of block 0 before it starts streaming: nobody else touches these
+// scalars while a mat-vec is running, so rsold / iter advance without a race.
+__device__ __forceinline__ void advance_state(const GemvArgs &a, int lane)
+{
+    const double s = warp_det_sum(a.rrpart, a.nchunks, lane);
+    if (lane == 0) {
+        State *st = a.st;
+        const long long it = st->iter;
+        if (it >= 0 && a.hist) a.hist[it] = s; // r'r of loop index `it`
+        st->rsold = s;                          // cg.cc:132 rsold = rsnew (cg.cc:91 when it == -1)
+        st->rsnew = s;
+        st->iter = it + 1;
+    }
+}
+
 // ------------------------------------------------------------------ programmatic dependent launch
 // A kernel launched with the programmatic-stream-serialization attribute may become resident
 // before its predecessor has finished; everything it reads from the predecessor must come

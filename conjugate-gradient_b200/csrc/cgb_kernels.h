@@ -43,6 +43,11 @@ const GemvVariant &gemv_variant(int i);
 cudaError_t launch_read_stream(const double *A, long long ndoubles, double *sink, int sm_count,
                                cudaStream_t s);
 
+// ---- reference-topology mat-vec (compat.cu): NUM_THREADS / BLOCK_WIDTH honoured literally ----
+size_t compat_part_doubles(long long n, int block_width);
+cudaError_t launch_compat_matvec(const GemvArgs &a, int nblk, int num_threads, int block_width,
+                                 int transposed, double *part /* compat_part_doubles */, cudaStream_t s);
+
 // ---- vector kernels (vec.cu) -------------------------------------------------------
 // load every kernel of the solve path now instead of at first launch
 cudaError_t preload_vec_kernels();

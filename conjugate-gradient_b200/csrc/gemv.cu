@@ -25,21 +25,6 @@
 
 namespace cgb {
 
-// Called by one full warp of block 0 before it starts streaming: nobody else touches these
-// scalars while a mat-vec is running, so rsold / iter advance without a race.
-__device__ __forceinline__ void advance_state(const GemvArgs &a, int lane)
-{
-    const double s = warp_det_sum(a.rrpart, a.nchunks, lane);
-    if (lane == 0) {
-        State *st = a.st;
-        const long long it = st->iter;
-        if (it >= 0 && a.hist) a.hist[it] = s; // r'r of loop index `it`
-        st->rsold = s;                          // cg.cc:132 rsold = rsnew (cg.cc:91 when it == -1)
-        st->rsnew = s;
-        st->iter = it + 1;
-    }
-}
-
 // One result (a row of Ap, or the block partial of p'Ap) into the gather buffer: locally, or --
 // fused exchange -- as a self-flagging LL entry straight into every rank's buffer over NVLink
 // (peer stores).  That store IS the all-gather: no fence, no flag, no collective kernel.

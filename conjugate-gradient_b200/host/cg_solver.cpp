@@ -218,13 +218,21 @@ int gemv_variant_for(int NUM_THREADS, int BLOCK_WIDTH)
 
 void CGSolver::solve(double *x, int NUM_THREADS, int BLOCK_WIDTH, bool T)
 {
+    // CGB_KERNEL=compat: run the reference program's own mat-vec topologies (MatVecT / MatVec)
+    // with NUM_THREADS / BLOCK_WIDTH taken literally -- the sweep curve of results/CUDA_T.txt.
+    // Default: the knobs pick the nearest launch shape of the product mat-vec.
+    const char *kernel = std::getenv("CGB_KERNEL");
+    const bool compat = kernel && std::string(kernel) == "compat";
     const int v = gemv_variant_for(NUM_THREADS, BLOCK_WIDTH);
     for (cgb_ctx *c : m_ctx) {
-        cgb_set_option(c, "gemv_variant", v);
+        int rc = 0;
+        if (!compat && (rc = cgb_set_option(c, "gemv_variant", v))) raise("cgb_set_option(gemv_variant)", rc);
         cgb_set_option(c, "num_threads", NUM_THREADS);
         cgb_set_option(c, "block_width", BLOCK_WIDTH);
         cgb_set_option(c, "transposed", T ? 1 : 0);
+        if ((rc = cgb_set_option(c, "compat", compat ? 1 : 0))) raise("cgb_set_option(compat)", rc);
     }
     std::memset(x, 0, sizeof(double) * (size_t)m_n); // fill<<<>>>(m_n, x, 0.0), cg.cu:217
     run_solve(x, m_n);                                // for (; k < m_n; ++k), cg.cu:236
+    if (compat) m_stats.gemv_variant = std::string("compat_") + (T ? "column" : "row");
 }

@@ -114,7 +114,11 @@ int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
  * "pdl": 0/1 programmatic dependent launch between the kernels of the iteration (the next
  * mat-vec prefetches A while the vector updates still run);
  * "exchange": 0 ncclAllGather / 1 fused peer stores (see cgb_exchange_import);
- * "transposed": the reference's true/false kernel switch (accepted, A is symmetric). */
+ * "transposed": the reference's true/false kernel switch (accepted, A is symmetric);
+ * "compat": 1 = run the mat-vec in the reference CUDA program's own topologies (MatVecT /
+ * MatVec, code/CUDA/cg.cu:14-110) with num_threads / block_width / transposed honoured
+ * literally but a deterministic chunk reduction instead of atomicAdd -- single GPU, for the
+ * NUM_THREADS x BLOCK_WIDTH sweep of BASELINE.json config 5; set the three knobs first. */
 int cgb_set_option(cgb_ctx *ctx, const char *key, int64_t value);
 int cgb_get_option(cgb_ctx *ctx, const char *key, int64_t *value);
 int cgb_gemv_variant_count(void);

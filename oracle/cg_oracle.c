@@ -92,10 +92,31 @@ double cgo_row_dot(const double *a, const double *p, int64_t n)
     return butterfly32(lane);
 }
 
+/* Order of the reference-topology ("compat") mat-vec, conjugate-gradient_b200/csrc/compat.cu:
+ * the row is cut into chunks of `bw` columns (MatVec: BLOCK_WIDTH columns per block, cg.cu:44-55;
+ * MatVecT: BLOCK_WIDTH rows per block, cg.cu:93-104 -- the same products because A is symmetric),
+ * each chunk a sequential fma chain from 0, the chunks added in ascending order from 0. */
+static int g_gemv_chunk = 0; /* 0 = lane order */
+void cgo_set_gemv_chunk(int block_width) { g_gemv_chunk = block_width > 0 ? block_width : 0; }
+
+static double row_dot_chunked(const double *a, const double *p, int64_t n, int64_t bw)
+{
+    double y = 0.0;
+    for (int64_t c0 = 0; c0 < n; c0 += bw) {
+        int64_t c1 = (c0 + bw < n) ? c0 + bw : n;
+        double s = 0.0;
+        for (int64_t k = c0; k < c1; ++k) s = fma(a[k], p[k], s);
+        y = y + s;
+    }
+    return y;
+}
+
 void cgo_gemv(int64_t rows, int64_t n, const double *A, int64_t ld, const double *p, double *y)
 {
+    const int64_t bw = g_gemv_chunk;
 #pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < rows; ++i) y[i] = cgo_row_dot(A + i * ld, p, n);
+    for (int64_t i = 0; i < rows; ++i)
+        y[i] = bw > 0 ? row_dot_chunked(A + i * ld, p, n, bw) : cgo_row_dot(A + i * ld, p, n);
 }
 
 double cgo_det_sum(const double *v, int64_t n)

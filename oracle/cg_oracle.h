@@ -67,6 +67,11 @@ double cgo_row_dot(const double *a_row, const double *p, int64_t n);
 /* y[0..rows) = A[rows x n, ld] . p, lane order per row */
 void cgo_gemv(int64_t rows, int64_t n, const double *A, int64_t ld, const double *p, double *y);
 
+/* select the mat-vec order used by cgo_gemv / cgo_solve / cgo_residual_check: 0 = lane order
+ * (the product kernels), bw > 0 = the reference-topology order with BLOCK_WIDTH = bw
+ * (csrc/compat.cu; see cg_oracle.c).  Process-global; tests reset it to 0. */
+void cgo_set_gemv_chunk(int block_width);
+
 double cgo_det_sum(const double *v, int64_t n);
 /* two-level dot of the global vectors a.b: chunk256 partials -> det_sum */
 double cgo_dot(const double *a, const double *b, int64_t n);

@@ -50,6 +50,7 @@ def lib():
         L.cgo_row_dot.argtypes = [_dp, _dp, C.c_int64]
         L.cgo_row_dot.restype = C.c_double
         L.cgo_gemv.argtypes = [C.c_int64, C.c_int64, _dp, C.c_int64, _dp, _dp]
+        L.cgo_set_gemv_chunk.argtypes = [C.c_int]
         L.cgo_det_sum.argtypes = [_dp, C.c_int64]
         L.cgo_det_sum.restype = C.c_double
         L.cgo_dot.argtypes = [_dp, _dp, C.c_int64]
@@ -102,6 +103,19 @@ def gemv(A: np.ndarray, p: np.ndarray) -> np.ndarray:
     y = np.empty(rows, dtype=np.float64)
     lib().cgo_gemv(rows, n, _p(A), A.strides[0] // 8, _p(p), _p(y))
     return y
+
+
+class gemv_chunk:
+    """with gemv_chunk(bw): ... -- the reference-topology mat-vec order (csrc/compat.cu)."""
+
+    def __init__(self, block_width: int):
+        self.bw = block_width
+
+    def __enter__(self):
+        lib().cgo_set_gemv_chunk(self.bw)
+
+    def __exit__(self, *exc):
+        lib().cgo_set_gemv_chunk(0)
 
 
 def det_sum(v: np.ndarray) -> float:

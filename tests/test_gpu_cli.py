@@ -76,6 +76,23 @@ def test_form2_matrix_market(O, tmp_path):
         assert 0 < float(row.split(",")[2]) < 60
 
 
+def test_form2_compat_kernel_mode(O, tmp_path):
+    """CGB_KERNEL=compat: the reference's own launch topologies, NUM_THREADS / BLOCK_WIDTH
+    literal; the printed numbers are the oracle's for that chunked order."""
+    mtx = str(tmp_path / "lap30.mtx")
+    O.write_lap2d_5pt_mtx(mtx, 30)
+    A = O.read_mtx_dense(mtx)
+    n = A.shape[0]
+    out = tmp_path / "res.txt"
+    for nt, bw, t in (("64", "16", "true"), ("8", "900", "false")):
+        with O.gemv_chunk(int(bw)):
+            ref = O.solve(A, O.init_source_term(n), max_iter=n, nranks=1, nblk=148)
+        r = _run([mtx, nt, bw, t, str(out)], env={"CGB_KERNEL": "compat"})
+        assert r.returncode == 0, r.stderr
+        assert _step_line(r.stdout) == O.debug_line(ref.k, ref.rsold, ref.norm_x, ref.rel_resid)
+    assert [row.split(",")[:2] for row in out.read_text().splitlines()] == [["64", "16"], ["8", "900"]]
+
+
 def test_multi_gpu_cli_psize_column(O, tmp_path, cgb):
     if cgb.device_count() < 2:
         pytest.skip("needs 2 GPUs")

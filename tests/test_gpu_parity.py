@@ -271,3 +271,54 @@ def test_n_beyond_int32_indexing(cgb, O):
     true_resid = rr * np.linalg.norm(b)
     assert abs(true_resid - np.sqrt(info.rsold)) <= 1e-9 * true_resid
     assert abs(nx - np.linalg.norm(x)) <= 1e-12 * nx
+
+
+# --------------------------------------------------------------------------- reference topologies
+@pytest.mark.parametrize("nt,bw", [(32, 1), (64, 16), (1000, 4096), (7, 5), (256, 1024)])
+def test_compat_topologies_bitwise_vs_oracle(cgb, O, nt, bw):
+    """Option "compat": the reference's column (MatVecT) and row (MatVec) launch topologies with
+    NUM_THREADS / BLOCK_WIDTH literal (csrc/compat.cu).  Both give the oracle's chunked order
+    bit for bit -- mat-vec, block partials and a whole solve -- for any launch shape, where the
+    reference's atomicAdd version is run-to-run non-deterministic."""
+    n = 1030
+    rng = _rng(bw)
+    A = O.generate_lap2d(n) + np.diag(rng.standard_normal(n) * 0.01)   # symmetric, non-trivial values
+    p = rng.standard_normal(n)
+    b = O.init_source_term(n)
+    with O.gemv_chunk(bw):
+        y_ref = O.gemv(A, p)
+        ref = O.solve(A, b, max_iter=60, nranks=1, nblk=148)
+    results = []
+    for transposed in (1, 0):
+        with _ctx(cgb, n) as ctx:
+            ctx.set_matrix_rows(A)
+            ctx.set_rhs(b)
+            ctx.set_option("num_threads", nt)
+            ctx.set_option("block_width", bw)
+            ctx.set_option("transposed", transposed)
+            ctx.set_option("compat", 1)
+            assert ctx.layout().nblk == 148
+            y, bp, pap = ctx.gemv(p, want_partials=True)
+            assert np.array_equal(y, y_ref), (transposed, nt, bw)
+            bp_ref = np.array([O.det_sum((p * y_ref)[slice(*O.block_range(n, 148, c))]) for c in range(148)])
+            assert np.array_equal(bp, bp_ref) and pap == O.det_sum(bp_ref)
+            x = np.zeros(n)
+            info, hist = ctx.solve(x, max_iter=60, tol=1e-10, history=True)
+            assert info.k == ref.k and np.array_equal(hist, ref.hist) and np.array_equal(x, ref.x)
+            results.append((x, hist))
+    assert np.array_equal(results[0][0], results[1][0])     # column == row topology (A symmetric)
+
+
+def test_compat_option_validation(cgb):
+    with _ctx(cgb, 64) as ctx:
+        with pytest.raises(cgb.CgbError):
+            ctx.set_option("compat", 1)                      # knobs not set
+        ctx.set_option("num_threads", 2048)
+        ctx.set_option("block_width", 16)
+        with pytest.raises(cgb.CgbError):
+            ctx.set_option("compat", 1)                      # NUM_THREADS > 1024 cannot launch
+        ctx.set_option("num_threads", 128)
+        ctx.set_option("compat", 1)
+        assert ctx.get_option("compat") == 1
+        ctx.set_option("block_width", 4)                     # changing a knob drops compat
+        assert ctx.get_option("compat") == 0
