@@ -75,3 +75,17 @@ def test_product_never_imports_the_oracle():
                     assert not hits, (f, needle, hits[:2])
     for f in ("include/cgb200.h",):
         assert "cg_oracle" not in open(os.path.join(ROOT, f)).read()
+
+
+def test_missing_library_fails_loudly(cgb, monkeypatch):
+    """Without libcgb200.so the binding raises (pointing at the build step) instead of
+    computing anything another way."""
+    import importlib
+    capi = importlib.import_module("conjugate-gradient_b200._capi")
+    monkeypatch.setattr(capi, "_lib", None)
+    monkeypatch.setattr(capi, "LIB_PATH", "/nonexistent/libcgb200.so")
+    with pytest.raises(cgb.CgbError) as ei:
+        capi.load()
+    assert "no CPU fallback" in str(ei.value)
+    with pytest.raises(cgb.CgbError):
+        capi.partition(10, 2)
