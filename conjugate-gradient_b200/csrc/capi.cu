@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <mutex>
 #include <new>
 #include <string>
 #include <unistd.h>
@@ -70,9 +71,11 @@ struct Nccl {
     int (*GetVersion)(int *) = nullptr;
 };
 Nccl g_nccl;
+std::mutex g_nccl_mu; // ranks may be threads of one process
 
 int load_nccl()
 {
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
     if (g_nccl.h) return CGB_OK;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     void *h = nullptr;
