@@ -159,3 +159,30 @@ def test_mtx_reader_restatement(O, tmp_path):
         O.read_mtx_dense(str(p))
     with pytest.raises(O.MtxError):
         O.read_mtx_dense(str(tmp_path / "missing.mtx"))
+
+
+def test_compat_chunk_order(O):
+    """The reference-topology order (csrc/compat.cu): chunks of BLOCK_WIDTH columns, each a
+    sequential fma chain, added in ascending order -- and lane order again afterwards."""
+    import math
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((5, 70))
+    p = rng.standard_normal(70)
+    lane = O.gemv(A, p)
+    with O.gemv_chunk(16):
+        y = O.gemv(A, p)
+    for i in range(5):
+        tot = 0.0
+        for c0 in range(0, 70, 16):
+            s = 0.0
+            for k in range(c0, min(c0 + 16, 70)):
+                s = math.fma(A[i, k], p[k], s) if hasattr(math, "fma") else s + A[i, k] * p[k]
+            tot = tot + s
+        if hasattr(math, "fma"):
+            assert y[i] == tot
+        else:
+            assert abs(y[i] - tot) <= 1e-13 * abs(tot)
+    assert np.array_equal(O.gemv(A, p), lane)          # the mode is reset on exit
+    with O.gemv_chunk(70):                              # one chunk = plain sequential fma dot
+        y1 = O.gemv(A, p)
+    np.testing.assert_allclose(y1, A @ p, rtol=1e-13)
