@@ -257,7 +257,7 @@ def product_arm(args):
         wiring.wire(ctx, rank, world, dist, cgb.unique_id)
     if args.variant is not None:
         ctx.set_option("gemv_variant", args.variant)
-    for key in ("graph", "graph_unroll", "poll_every", "exchange"):
+    for key in ("graph", "graph_unroll", "poll_every", "exchange", "pdl", "l2_prefetch"):
         v = getattr(args, key)
         if v is not None:
             ctx.set_option(key, v)
@@ -396,7 +396,7 @@ def product_arm(args):
     if rank == 0:
         cfg = base_config(args.workload, n, world)
         cfg.update({"gemv_variant": roofline["kernel"], "nblk": lay.nblk,
-                    "graph": ctx_opts(args), "parallelism": "rows%d" % world,
+                    "options": ctx_opts(args), "parallelism": "rows%d" % world,
                     "exchange": exchange_name})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -415,7 +415,7 @@ def product_arm(args):
 
 
 def ctx_opts(args):
-    return {k: getattr(args, k) for k in ("graph", "graph_unroll", "poll_every", "exchange")
+    return {k: getattr(args, k) for k in ("graph", "graph_unroll", "poll_every", "exchange", "pdl", "l2_prefetch")
             if getattr(args, k) is not None} or "defaults"
 
 
@@ -433,6 +433,8 @@ def main():
     ap.add_argument("--graph-unroll", dest="graph_unroll", type=int, default=None)
     ap.add_argument("--poll-every", dest="poll_every", type=int, default=None)
     ap.add_argument("--exchange", type=int, default=None)
+    ap.add_argument("--pdl", type=int, default=None)
+    ap.add_argument("--l2-prefetch", dest="l2_prefetch", type=int, default=None)
     ap.add_argument("--cpu-iters", dest="cpu_iters", type=int, default=40)
     ap.add_argument("--cpu-ranks", dest="cpu_ranks", type=int, default=1,
                     help="MPI ranks of the CPU reference (forked on this host; default 1 rank x all threads)")

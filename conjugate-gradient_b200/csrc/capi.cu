@@ -116,7 +116,7 @@ struct cgb_ctx {
     int opt_compat = 0;            // 1: the reference's mat-vec topologies (compat.cu)
     double *compat_part = nullptr; // chunk partials of the compat mat-vec
     size_t compat_part_cap = 0;
-    int poll_every = 16, graph_unroll = 16, opt_pdl = 1;
+    int poll_every = 16, graph_unroll = 16, opt_pdl = 1, opt_l2_prefetch = 0;
 
     double *A = nullptr, *p = nullptr, *r = nullptr, *x = nullptr, *b = nullptr;
     double *apx = nullptr, *rrpart = nullptr, *scratch = nullptr, *hist = nullptr, *sink = nullptr;
@@ -198,6 +198,7 @@ GemvArgs make_gemv_args(const cgb_ctx *c, const double *v, int advance)
     a.hist = c->hist;
     a.advance = advance;
     a.pdl = (advance && c->opt_pdl && !c->opt_profile) ? 1 : 0; // only inside the CG loop
+    a.l2_prefetch = a.pdl ? c->opt_l2_prefetch : 0;
     return a;
 }
 
@@ -754,6 +755,10 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
     } else if (k == "pdl") {
         c->opt_pdl = value != 0;
         drop_graph(c);
+    } else if (k == "l2_prefetch") {
+        if (value < 0 || value > 64) return fail(CGB_ERR_INVALID, "l2_prefetch must be in [0, 64] pipeline steps");
+        c->opt_l2_prefetch = (int)value;
+        drop_graph(c);
     } else if (k == "exchange") {
         if (value != 0 && value != 1) return fail(CGB_ERR_INVALID, "exchange must be 0 (nccl) or 1 (fused p2p)");
         if (c->world > 1 && value == 1 && !c->p2p_ready)
@@ -790,6 +795,7 @@ extern "C" int cgb_get_option(cgb_ctx *c, const char *key, int64_t *value)
     else if (k == "graph_unroll") *value = c->graph_unroll;
     else if (k == "compat") *value = c->opt_compat;
     else if (k == "pdl") *value = c->opt_pdl;
+    else if (k == "l2_prefetch") *value = c->opt_l2_prefetch;
     else if (k == "exchange") *value = c->opt_exchange;
     else if (k == "num_threads") *value = c->opt_num_threads;
     else if (k == "block_width") *value = c->opt_block_width;

@@ -73,6 +73,7 @@ struct GemvArgs {
     double *hist;         // nullable
     int advance;          // 1 inside the CG loop, 0 for the init / DEBUG mat-vecs
     int pdl;              // host side: launch with the programmatic-dependent-launch attribute
+    int l2_prefetch;      // pipeline steps of A prefetched into L2 before the dependency wait
 };
 
 // ------------------------------------------------------------------ reductions
@@ -305,6 +306,11 @@ __device__ __forceinline__ void bulk_g2s_nohint(void *dst_smem, const void *src,
             smem_u32(dst_smem)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+// Asynchronous prefetch of `bytes` (multiple of 16) into L2 through the TMA unit; no completion.
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {

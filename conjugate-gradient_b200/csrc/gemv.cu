@@ -107,6 +107,20 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
         };
         const unsigned npro = total < (unsigned)STAGES ? total : (unsigned)STAGES;
         for (unsigned it = 0; it < npro; ++it) issue(it, true, false);   // A only: no dependency
+        // While the vector updates (and, multi-GPU, the exchange) of the previous iteration
+        // finish, HBM would idle once the ring is full: pull the next steps of A into L2.
+        if (a.l2_prefetch > 0) {
+            const unsigned npf = (total - npro < (unsigned)a.l2_prefetch) ? total : npro + (unsigned)a.l2_prefetch;
+            for (unsigned it = npro; it < npf; ++it) {
+                const int b = (int)(it / (unsigned)ntc), t = (int)(it - (unsigned)b * (unsigned)ntc);
+                const long long rb0 = r0 + (long long)b * nrows / nb;
+                const int nr = (int)(r0 + (long long)(b + 1) * nrows / nb - rb0);
+                const long long c0 = (long long)t * TC;
+                const int w = (int)((a.ld - c0 < TC) ? (a.ld - c0) : TC);
+                for (int j = lane; j < nr; j += 32)
+                    bulk_prefetch_l2(a.A + (rb0 + j) * a.ld + c0, (unsigned)(w * 8));
+            }
+        }
         griddep_wait();                                                    // p is final from here on
         const int done = a.st->done;
         for (unsigned it = 0; it < npro; ++it) issue(it, false, true);

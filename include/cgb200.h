@@ -112,7 +112,8 @@ int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
  * reference CUDA program (code/CUDA/cg_main.cc:21-25), mapped onto threads per CTA and
  * column-tile width of the mat-vec; "graph": 0/1 CUDA-graph replay of the iteration;
  * "pdl": 0/1 programmatic dependent launch between the kernels of the iteration (the next
- * mat-vec prefetches A while the vector updates still run);
+ * mat-vec prefetches A while the vector updates still run); "l2_prefetch": pipeline steps of A
+ * the mat-vec additionally pulls into L2 before that wait (0 = off);
  * "exchange": 0 ncclAllGather / 1 fused peer stores (see cgb_exchange_import);
  * "transposed": the reference's true/false kernel switch (accepted, A is symmetric);
  * "compat": 1 = run the mat-vec in the reference CUDA program's own topologies (MatVecT /
