@@ -116,7 +116,7 @@ struct cgb_ctx {
     int opt_compat = 0;            // 1: the reference's mat-vec topologies (compat.cu)
     double *compat_part = nullptr; // chunk partials of the compat mat-vec
     size_t compat_part_cap = 0;
-    int poll_every = 16, graph_unroll = 16, opt_pdl = 1, opt_l2_prefetch = 0;
+    int poll_every = 16, graph_unroll = 16, opt_pdl = 1, opt_l2_prefetch = 4;
 
     double *A = nullptr, *p = nullptr, *r = nullptr, *x = nullptr, *b = nullptr;
     double *apx = nullptr, *rrpart = nullptr, *scratch = nullptr, *hist = nullptr, *sink = nullptr;
