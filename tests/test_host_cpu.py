@@ -138,3 +138,37 @@ def test_cgsolver_usage_and_no_gpu_errors(tmp_path):
         r = subprocess.run([CGSOLVER, "64", str(out)], capture_output=True, text=True, timeout=60)
         assert r.returncode == 2 and "cgb_create failed" in r.stderr
         assert not out.exists()
+
+
+def test_reader_randomised_against_the_reference_reader(O, tmp_path):
+    """40 seeded random coordinate files (general / symmetric, duplicates, comment blocks,
+    mixed number formats, ragged whitespace): product reader == the reference's own reader
+    == the oracle's restatement, entry for entry and densified."""
+    _need(DUMP)
+    rng = np.random.default_rng(2024)
+    for case in range(40):
+        n = int(rng.integers(1, 12))
+        sym = bool(rng.integers(0, 2))
+        nz = int(rng.integers(0, 3 * n + 1))
+        lines = ["%%MatrixMarket matrix coordinate real " + ("symmetric" if sym else "general")]
+        for _ in range(int(rng.integers(0, 4))):
+            lines.append("% " + "x" * int(rng.integers(0, 30)))
+        lines.append("%d %d %d" % (n, n, nz))
+        for _ in range(nz):
+            i, j = int(rng.integers(1, n + 1)), int(rng.integers(1, n + 1))
+            if sym and j > i:
+                i, j = j, i
+            v = float(rng.standard_normal()) * 10.0 ** int(rng.integers(-3, 4))
+            fmt = ["%d %d %.17g", "%d  %d   %e", " %d %d %g", "%d\t%d\t%.3f"][int(rng.integers(0, 4))]
+            lines.append(fmt % (i, j, v))
+        src = tmp_path / ("r%02d.mtx" % case)
+        src.write_text("\n".join(lines) + "\n")
+        assert _dump(DUMP, str(src), str(tmp_path / "p.bin")).returncode == 0
+        assert _dump(DUMP, str(src), str(tmp_path / "pd.bin"), dense=True).returncode == 0
+        dense = _read_dense(str(tmp_path / "pd.bin"))
+        assert np.array_equal(dense, O.read_mtx_dense(str(src))), case
+        if os.path.exists(REF_DUMP):
+            assert _dump(REF_DUMP, str(src), str(tmp_path / "r.bin")).returncode == 0
+            assert _dump(REF_DUMP, str(src), str(tmp_path / "rd.bin"), dense=True).returncode == 0
+            assert open(str(tmp_path / "p.bin"), "rb").read() == open(str(tmp_path / "r.bin"), "rb").read(), case
+            assert np.array_equal(dense, _read_dense(str(tmp_path / "rd.bin"))), case
