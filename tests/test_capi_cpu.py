@@ -89,3 +89,37 @@ def test_missing_library_fails_loudly(cgb, monkeypatch):
     assert "no CPU fallback" in str(ei.value)
     with pytest.raises(cgb.CgbError):
         capi.partition(10, 2)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/cgb200.h compiles as strict C99 and the library links from a plain C program --
+    the boundary a cgo / JNI / ctypes binding would use (no C++ or torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    lib_dir = os.path.join(ROOT, "conjugate-gradient_b200")
+    if not gcc or not os.path.exists(os.path.join(lib_dir, "libcgb200.so")):
+        pytest.skip("gcc or libcgb200.so missing")
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include "cgb200.h"
+#include <stdio.h>
+int main(void) {
+    int64_t s[3], c[3];
+    double b[4];
+    cgb_ctx *ctx = NULL;
+    int ndev = -1, rc;
+    if (cgb_partition(10, 3, s, c) != CGB_OK) return 1;
+    if (cgb_init_source_term(4, 0.25, b) != CGB_OK || b[0] != 0.0) return 2;
+    rc = cgb_device_count(&ndev);
+    if (rc != CGB_OK && cgb_create(16, 0, 1, 0, &ctx) != CGB_ERR_NO_DEVICE) return 3;
+    printf("%d %lld %lld %lld\n", cgb_abi_version(), (long long)c[0], (long long)c[1], (long long)c[2]);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    subprocess.check_call([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-L", lib_dir, "-lcgb200", "-Wl,-rpath," + lib_dir, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.split() == ["1", "3", "3", "4"]
