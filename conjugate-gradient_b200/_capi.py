@@ -72,6 +72,7 @@ SIGNATURES = [
     ("cgb_bench_read", C.c_int, [_CTX, C.c_int, C.POINTER(C.c_float)]),
     ("cgb_last_gemv_timing", C.c_int, [_CTX, C.POINTER(C.c_float), _i64p]),
     ("cgb_launch_count", C.c_int, [_CTX, _i64p]),
+    ("cgb_trace_read", C.c_int, [_CTX, C.c_int, C.POINTER(C.c_uint64), C.c_int64, _i64p, _i64p]),
 ]
 
 _lib = None
@@ -274,6 +275,24 @@ class Context:
         ms, n = C.c_float(), C.c_int64()
         _check(self._lib.cgb_last_gemv_timing(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def trace_read(self, which: int):
+        """(records[L, blocks, 8] uint64 in launch order, launches seen) of the diagnostic
+        timeline of kernel `which` (0 mat-vec, 1 update_xr, 2 update_p); option "trace" = L."""
+        cap = self.get_option("trace")
+        lay = self.layout()
+        nb = lay.nblk if which == 0 else lay.nchunks
+        buf = np.zeros(cap * nb * 8, dtype=np.uint64)
+        seen, blocks = C.c_int64(), C.c_int64()
+        _check(self._lib.cgb_trace_read(self._h, which, buf.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                        buf.size, C.byref(seen), C.byref(blocks)))
+        rec = buf.reshape(cap, blocks.value, 8)
+        n = seen.value
+        if n >= cap:   # ring: oldest kept launch first
+            rec = np.roll(rec, -(n % cap), axis=0)
+        else:
+            rec = rec[:n]
+        return rec, n
 
     def launch_count(self) -> int:
         n = C.c_int64()

@@ -117,6 +117,12 @@ struct cgb_ctx {
     double *compat_part = nullptr; // chunk partials of the compat mat-vec
     size_t compat_part_cap = 0;
     int poll_every = 16, graph_unroll = 16, opt_pdl = 1, opt_l2_prefetch = 4;
+    int opt_loopback = 0;          // profiling: this rank plays every rank of the exchange (see "loopback")
+    // diagnostic timelines (option "trace"): 0 = mat-vec, 1 = update_xr, 2 = update_p
+    unsigned long long *trace_buf[3] = {nullptr, nullptr, nullptr};
+    unsigned int *trace_cnt[3] = {nullptr, nullptr, nullptr};
+    int trace_blocks[3] = {0, 0, 0}; // capacity in blocks per launch
+    int trace_cap = 0;
 
     double *A = nullptr, *p = nullptr, *r = nullptr, *x = nullptr, *b = nullptr;
     double *apx = nullptr, *rrpart = nullptr, *scratch = nullptr, *hist = nullptr, *sink = nullptr;
@@ -174,6 +180,17 @@ Gather make_gather(const cgb_ctx *c)
     return g;
 }
 
+Trace make_trace(const cgb_ctx *c, int which, int blocks)
+{
+    Trace t;
+    t.buf = c->trace_buf[which];
+    t.cnt = c->trace_cnt[which];
+    t.cap = c->trace_cap;
+    t.nblk = blocks;
+    if (blocks > c->trace_blocks[which]) t.buf = nullptr; // cannot happen: sized for the largest grid
+    return t;
+}
+
 GemvArgs make_gemv_args(const cgb_ctx *c, const double *v, int advance)
 {
     GemvArgs a;
@@ -199,6 +216,9 @@ GemvArgs make_gemv_args(const cgb_ctx *c, const double *v, int advance)
     a.advance = advance;
     a.pdl = (advance && c->opt_pdl && !c->opt_profile) ? 1 : 0; // only inside the CG loop
     a.l2_prefetch = a.pdl ? c->opt_l2_prefetch : 0;
+    if (c->opt_loopback) // every "peer" is this rank's own buffer, shifted so that slot g is hit
+        for (int g = 0; g < c->world; ++g) a.peer_ll[g] = c->ll + ((long long)g - c->rank) * c->slot;
+    if (c->trace_cap > 0 && advance) a.trace = make_trace(c, 0, c->nblk);
     return a;
 }
 
@@ -219,6 +239,10 @@ VecArgs make_vec_args(const cgb_ctx *c)
     a.n = c->n;
     a.tol = c->tol;
     a.pdl = (c->opt_pdl && !c->opt_profile) ? 1 : 0;
+    if (c->trace_cap > 0) {
+        a.trace_xr = make_trace(c, 1, (int)c->nchunks);
+        a.trace_p = make_trace(c, 2, (int)c->nchunks);
+    }
     return a;
 }
 
@@ -227,6 +251,18 @@ void set_variant(cgb_ctx *c, int v)
     c->variant = v;
     c->nblk = c->sm_count * gemv_variant(v).ctas_per_sm;
     c->slot = (c->maxrows + c->nblk + 1) & ~1LL;
+}
+
+void free_trace(cgb_ctx *c)
+{
+    for (int w = 0; w < 3; ++w) {
+        if (c->trace_buf[w]) cudaFree(c->trace_buf[w]);
+        if (c->trace_cnt[w]) cudaFree(c->trace_cnt[w]);
+        c->trace_buf[w] = nullptr;
+        c->trace_cnt[w] = nullptr;
+        c->trace_blocks[w] = 0;
+    }
+    c->trace_cap = 0;
 }
 
 void drop_graph(cgb_ctx *c)
@@ -469,6 +505,7 @@ extern "C" int cgb_destroy(cgb_ctx *c)
         if (p) cudaFree(p);
     if (c->st) cudaFree(c->st);
     if (c->compat_part) cudaFree(c->compat_part);
+    free_trace(c);
     if (c->ll) cudaFree(c->ll);
     if (c->ctl) cudaFree(c->ctl);
     if (c->h_done) cudaFreeHost(c->h_done);
@@ -759,6 +796,46 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
         if (value < 0 || value > 64) return fail(CGB_ERR_INVALID, "l2_prefetch must be in [0, 64] pipeline steps");
         c->opt_l2_prefetch = (int)value;
         drop_graph(c);
+    } else if (k == "trace") {
+        // keep %globaltimer timelines of the last `value` launches of the loop kernels (0 = off)
+        if (value < 0 || value > 4096) return fail(CGB_ERR_INVALID, "trace must be in [0, 4096] launches");
+        int rc = use_device(c);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(c->stream));
+        free_trace(c);
+        drop_graph(c);
+        if (value > 0) {
+            int max_cps = 1;
+            for (int v = 0; v < gemv_variant_count(); ++v)
+                if (gemv_variant(v).ctas_per_sm > max_cps) max_cps = gemv_variant(v).ctas_per_sm;
+            const int blocks[3] = {c->sm_count * max_cps, (int)c->nchunks, (int)c->nchunks};
+            for (int w = 0; w < 3; ++w) {
+                const size_t words = (size_t)value * blocks[w] * kTraceWords;
+                CK(cudaMalloc(&c->trace_buf[w], words * sizeof(unsigned long long)));
+                CK(cudaMalloc(&c->trace_cnt[w], (size_t)blocks[w] * sizeof(unsigned int)));
+                CK(cudaMemset(c->trace_buf[w], 0, words * sizeof(unsigned long long)));
+                CK(cudaMemset(c->trace_cnt[w], 0, (size_t)blocks[w] * sizeof(unsigned int)));
+                c->trace_blocks[w] = blocks[w];
+            }
+            c->trace_cap = (int)value;
+        }
+    } else if (k == "loopback") {
+        // Profiling aid: one GPU runs ONE rank's shard of a `world`-way split under the production
+        // schedule, with every peer pointer of the fused exchange aimed at its own buffer (it
+        // fills all `world` slots itself).  Timing and traffic of that rank are real; the
+        // numbers it iterates on are not a CG solve.
+        if (value != 0) {
+            if (c->world < 2) return fail(CGB_ERR_INVALID, "loopback needs world > 1");
+            if (c->p2p_ready && !c->opt_loopback) return fail(CGB_ERR_STATE, "a real exchange is already imported");
+            c->opt_loopback = 1;
+            c->p2p_ready = true;
+            c->opt_exchange = 1;
+        } else if (c->opt_loopback) {
+            c->opt_loopback = 0;
+            c->p2p_ready = false;
+            c->opt_exchange = 0;
+        }
+        drop_graph(c);
     } else if (k == "exchange") {
         if (value != 0 && value != 1) return fail(CGB_ERR_INVALID, "exchange must be 0 (nccl) or 1 (fused p2p)");
         if (c->world > 1 && value == 1 && !c->p2p_ready)
@@ -797,6 +874,8 @@ extern "C" int cgb_get_option(cgb_ctx *c, const char *key, int64_t *value)
     else if (k == "pdl") *value = c->opt_pdl;
     else if (k == "l2_prefetch") *value = c->opt_l2_prefetch;
     else if (k == "exchange") *value = c->opt_exchange;
+    else if (k == "trace") *value = c->trace_cap;
+    else if (k == "loopback") *value = c->opt_loopback;
     else if (k == "num_threads") *value = c->opt_num_threads;
     else if (k == "block_width") *value = c->opt_block_width;
     else if (k == "transposed") *value = c->opt_transposed;
@@ -1126,5 +1205,25 @@ extern "C" int cgb_launch_count(cgb_ctx *c, int64_t *launches)
 {
     if (!c || !launches) return fail(CGB_ERR_INVALID, "null argument");
     *launches = c->kernel_launches;
+    return CGB_OK;
+}
+
+extern "C" int cgb_trace_read(cgb_ctx *c, int which, uint64_t *out, int64_t capacity_words,
+                              int64_t *launches, int64_t *blocks)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (which < 0 || which > 2) return fail(CGB_ERR_INVALID, "which must be 0 (mat-vec), 1 (update_xr) or 2 (update_p)");
+    if (c->trace_cap <= 0) return fail(CGB_ERR_STATE, "option \"trace\" is off");
+    const int nb = which == 0 ? c->nblk : (int)c->nchunks;
+    const int64_t words = (int64_t)c->trace_cap * nb * kTraceWords;
+    if (!out || capacity_words < words)
+        return fail(CGB_ERR_INVALID, "trace buffer too small: need %lld words", (long long)words);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, c->trace_buf[which], (size_t)words * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    unsigned int seen = 0;
+    CK(cudaMemcpy(&seen, c->trace_cnt[which], sizeof seen, cudaMemcpyDeviceToHost));
+    if (launches) *launches = seen;
+    if (blocks) *blocks = nb;
     return CGB_OK;
 }

@@ -51,6 +51,19 @@ struct Gather {
     int p2p;           // 1: fused mode
 };
 
+// Diagnostic timeline (option "trace" = launches kept): every CTA of a traced kernel stamps
+// %globaltimer at fixed points of its life into rec[(launch % cap) * nblk + cta][kTraceWords];
+// `cnt[cta]` counts the launches that CTA index has seen.  This is how the production schedule
+// (CUDA graph + programmatic dependent launch, where CUDA events cannot be placed between the
+// kernels) is timed: profiles/trace_iter.py, bench.py "production_launch_ms".
+constexpr int kTraceWords = 8;
+struct Trace {
+    unsigned long long *buf; // nullptr: tracing off
+    unsigned int *cnt;       // one launch counter per CTA index
+    int cap;                 // launches kept (ring)
+    int nblk;                // CTAs per launch
+};
+
 struct GemvArgs {
     const double *A;      // rows x ld shard, zero-padded columns
     const double *v;      // input vector, ld doubles, zero-padded
@@ -74,6 +87,7 @@ struct GemvArgs {
     int advance;          // 1 inside the CG loop, 0 for the init / DEBUG mat-vecs
     int pdl;              // host side: launch with the programmatic-dependent-launch attribute
     int l2_prefetch;      // pipeline steps of A prefetched into L2 before the dependency wait
+    Trace trace;          // diagnostic timeline (option "trace"); buf == nullptr: off
 };
 
 // ------------------------------------------------------------------ reductions
@@ -138,6 +152,24 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+// trace helpers: slot of this launch for CTA `cta` (one thread per CTA calls it once) ...
+__device__ __forceinline__ unsigned long long *trace_slot(const Trace &t, int cta)
+{
+    const unsigned k = atomicAdd(&t.cnt[cta], 1u);
+    return t.buf + ((size_t)(k % (unsigned)t.cap) * (size_t)t.nblk + (size_t)cta) * kTraceWords;
+}
+// ... and one stamp into it
+__device__ __forceinline__ void trace_stamp(unsigned long long *rec, int word)
+{
+    if (rec) rec[word] = globaltimer_ns();
+}
+__device__ __forceinline__ unsigned smid()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+
 // producer: one 16-byte store {lo, tag, hi, tag}; correct even if it tears into two 8-byte halves
 __device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned tag)
 {

@@ -63,6 +63,7 @@ struct VecArgs {
     long long n;
     double tol;
     int pdl;                 // host side: chain update_xr / update_p with programmatic dependent launch
+    Trace trace_xr, trace_p; // diagnostic timelines of update_xr / update_p (buf == nullptr: off)
 };
 // r = b - A x0 ; p = r ; rrpart = chunk partials of r.p             (cg.cc:77-92)
 cudaError_t launch_init_residual(const VecArgs &a, cudaStream_t s);

@@ -61,14 +61,21 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
     const int nb = (nrows + TR - 1) / TR;          // row blocks, balanced below
     const int ntc = (int)((a.ld + TC - 1) / TC);   // column tiles
 
+    __shared__ unsigned long long *s_rec; // diagnostic timeline record of this CTA (nullptr: off)
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], CW);
         }
         fence_mbar_init();
+        s_rec = a.trace.buf ? trace_slot(a.trace, c) : nullptr;
+        if (s_rec) {
+            s_rec[0] = globaltimer_ns();
+            s_rec[7] = (unsigned long long)smid() | ((unsigned long long)nrows << 32);
+        }
     }
     __syncthreads();
+    unsigned long long *const rec = s_rec;
 
     // Programmatic dependent launch: this grid may become resident while the previous kernels of
     // the iteration (update_xr / update_p, even the tail of the previous mat-vec) still run.
@@ -121,7 +128,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
                     bulk_prefetch_l2(a.A + (rb0 + j) * a.ld + c0, (unsigned)(w * 8));
             }
         }
+        if (lane == 0) trace_stamp(rec, 1);
         griddep_wait();                                                    // p is final from here on
+        if (lane == 0) trace_stamp(rec, 2);
         const int done = a.st->done;
         for (unsigned it = 0; it < npro; ++it) issue(it, false, true);
         if (done) {
@@ -134,6 +143,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
             mbar_wait(&empty[it % STAGES], ((it / STAGES) & 1u) ^ 1u);
             issue(it, true, true);
         }
+        if (lane == 0) trace_stamp(rec, 4);
     } else {
         // ===== consumers =====
         griddep_wait();
@@ -161,6 +171,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
                 const long long c0 = (long long)t * TC;
                 const int w = (int)((a.ld - c0 < TC) ? (a.ld - c0) : TC);
                 mbar_wait(&full[stage], ph);
+                if (rec && it == 0 && tid == 0) trace_stamp(rec, 3);
                 const double2 *sa2 = reinterpret_cast<const double2 *>(sA + (size_t)stage * TR * TC);
                 const double2 *sp2 = reinterpret_cast<const double2 *>(sP + (size_t)stage * TC);
                 if (nv == RPW && w == TC) {
@@ -205,10 +216,14 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
                 }
             }
         }
+        if (tid == 0) trace_stamp(rec, 5);
         named_bar_sync(1, CW * 32);
         if (warp == 0) {
             const double bp = warp_det_sum(qs, nrows, lane);
-            if (lane == 0) store_out(a, obase + a.maxrows + c, lbase + a.maxrows + c, tag, bp);
+            if (lane == 0) {
+                store_out(a, obase + a.maxrows + c, lbase + a.maxrows + c, tag, bp);
+                trace_stamp(rec, 6);
+            }
         }
     }
 }

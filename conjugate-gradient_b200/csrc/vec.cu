@@ -53,10 +53,17 @@ __global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a)
     extern __shared__ double sh_part[]; // world * nblk block partials
     __shared__ double wsum[8];
     __shared__ double sh_alpha;
+    const int tid = threadIdx.x;
+    // diagnostic timeline: thread 0 of every block stamps entry / dependency met / alpha known / exit
+    unsigned long long *rec = nullptr;
+    if (a.trace_xr.buf && tid == 0) {
+        rec = trace_slot(a.trace_xr, blockIdx.x);
+        trace_stamp(rec, 0);
+    }
     griddep_launch_dependents(); // let update_p (and, behind it, the next mat-vec) become resident
     griddep_wait();              // ... but read nothing before the mat-vec has completed
+    trace_stamp(rec, 1);
     if (a.st->done) return;
-    const int tid = threadIdx.x;
     // fused exchange: every read below polls its own LL entry until the owning rank's mat-vec
     // has delivered it over NVLink -- this kernel may start while peers are still streaming A
     const GatherView gv = gather_view(a.apx, a.g);
@@ -80,6 +87,7 @@ __global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a)
         }
     }
     __syncthreads();
+    trace_stamp(rec, 2);
     const double alpha = sh_alpha;
     const long long i = (long long)blockIdx.x * kChunk + tid;
     double v = 0.0;
@@ -93,6 +101,7 @@ __global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a)
     const double t = block_chunk256(v, wsum, tid);
     if (tid == 0) a.rrpart[blockIdx.x] = t;
     exchange_consumed(a.g, tid);
+    trace_stamp(rec, 3);
 }
 
 __global__ void __launch_bounds__(kChunk) update_p_kernel(const VecArgs a, long long nchunks)
@@ -101,8 +110,14 @@ __global__ void __launch_bounds__(kChunk) update_p_kernel(const VecArgs a, long 
     __shared__ double sh_bcast;
     __shared__ int sh_done;
     const int tid = threadIdx.x;
+    unsigned long long *rec = nullptr;
+    if (a.trace_p.buf && tid == 0) {
+        rec = trace_slot(a.trace_p, blockIdx.x);
+        trace_stamp(rec, 0);
+    }
     griddep_launch_dependents(); // the next mat-vec may start prefetching A now
     griddep_wait();              // update_xr has completed: rrpart and r are final
+    trace_stamp(rec, 1);
     // block 0 may raise `done` while this launch is still running: sample it once per block
     if (tid == 0) sh_done = a.st->done;
     __syncthreads();
@@ -122,6 +137,7 @@ __global__ void __launch_bounds__(kChunk) update_p_kernel(const VecArgs a, long 
     const double beta = __ddiv_rn(rsnew, a.st->rsold);                            // cg.cc:124
     const long long i = (long long)blockIdx.x * kChunk + tid;
     if (i < a.n) a.p[i] = __fma_rn(beta, a.p[i], a.r[i]);                         // cg.cc:127-129
+    trace_stamp(rec, 3);
 }
 
 __global__ void __launch_bounds__(32) finalize_kernel(const VecArgs a, long long nchunks)

@@ -115,6 +115,10 @@ int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
  * mat-vec prefetches A while the vector updates still run); "l2_prefetch": pipeline steps of A
  * the mat-vec additionally pulls into L2 before that wait (0 = off);
  * "exchange": 0 ncclAllGather / 1 fused peer stores (see cgb_exchange_import);
+ * "trace": launches kept by the diagnostic timeline (cgb_trace_read; 0 = off);
+ * "loopback": profiling aid -- a rank of world > 1 with no peers aims every peer pointer of the
+ * fused exchange at its own buffer, so ONE GPU runs one rank's shard under the production
+ * schedule (timing and traffic are real, the numbers are not a CG solve);
  * "transposed": the reference's true/false kernel switch (accepted, A is symmetric);
  * "compat": 1 = run the mat-vec in the reference CUDA program's own topologies (MatVecT /
  * MatVec, code/CUDA/cg.cu:14-110) with num_threads / block_width / transposed honoured
@@ -183,6 +187,17 @@ int cgb_bench_read(cgb_ctx *ctx, int reps, float *ms_avg);
 int cgb_last_gemv_timing(cgb_ctx *ctx, float *ms_avg, int64_t *launches);
 /* Kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 int cgb_launch_count(cgb_ctx *ctx, int64_t *launches);
+/* Diagnostic timeline of the iteration under its PRODUCTION schedule (CUDA graph + programmatic
+ * dependent launch, where no CUDA event can sit between the kernels).  With the option
+ * "trace" = L every CTA of the loop kernels stamps %globaltimer (ns) into a ring of the last L
+ * launches; this call copies the ring of kernel `which` (0 = mat-vec, 1 = x/r update, 2 = p
+ * update) to `out` as [L][*blocks][8] words and reports how many launches were seen in total.
+ * mat-vec words: 0 entry, 1 ring pre-filled, 2 dependency met (p final), 3 first tile
+ * consumed, 4 last tile issued, 5 rows done, 6 exit, 7 = smid | rows << 32.  vector kernels:
+ * 0 entry, 1 dependency met, 2 scalar known, 3 exit.  The replacement for what the reference
+ * measures with one chrono pair around solve (code/MPI/cg_main.cc:53-55). */
+int cgb_trace_read(cgb_ctx *ctx, int which, uint64_t *out, int64_t capacity_words,
+                   int64_t *launches, int64_t *blocks);
 
 #ifdef __cplusplus
 }
