@@ -117,6 +117,11 @@ struct cgb_ctx {
     double *compat_part = nullptr; // chunk partials of the compat mat-vec
     size_t compat_part_cap = 0;
     int poll_every = 16, graph_unroll = 16, opt_pdl = 1, opt_l2_prefetch = 4;
+    int opt_schedule = 1;          // 1: persistent cooperative kernel (persist.cu) when usable, 0: graph of 3 kernels
+    long long spin_timeout_ms = 20000; // bound of the device-side waits on other CTAs / ranks
+    PersistSync *psync = nullptr;
+    int smem_optin = 0;            // cudaDevAttrMaxSharedMemoryPerBlockOptin
+    long long persist_launches = 0;
     int opt_loopback = 0;          // profiling: this rank plays every rank of the exchange (see "loopback")
     // diagnostic timelines (option "trace"): 0 = mat-vec, 1 = update_xr, 2 = update_p
     unsigned long long *trace_buf[3] = {nullptr, nullptr, nullptr};
@@ -333,6 +338,87 @@ int build_graph(cgb_ctx *c)
     return CGB_OK;
 }
 
+// ---- persistent schedule (persist.cu) ------------------------------------------------
+// The persistent kernel exists for the tile shapes listed in persist.cu; it needs one CTA per SM,
+// the fused exchange (or one rank), at most persist_max_chunks() vector chunks per CTA and the
+// scratch for the block / chunk partials next to the tile ring in shared memory.
+int persist_index(const cgb_ctx *c)
+{
+    const char *name = gemv_variant(c->variant).name;
+    for (int i = 0; i < persist_variant_count(); ++i)
+        if (strcmp(persist_variant(i).name, name) == 0) return i;
+    return -1;
+}
+
+void persist_scratch(const cgb_ctx *c, int *qs_n, int *scr_n)
+{
+    const long long rpc = (c->rows + c->nblk - 1) / c->nblk;
+    long long scr = (long long)c->world * c->nblk;
+    if (c->nchunks > scr) scr = c->nchunks;
+    *qs_n = (int)((rpc + 1) & ~1LL);
+    *scr_n = (int)((scr + 1) & ~1LL);
+}
+
+// nullptr when the persistent schedule can run this context as configured, else the reason
+const char *persist_unusable(const cgb_ctx *c)
+{
+    if (c->opt_compat) return "compat mat-vec";
+    if (c->opt_profile) return "profile mode (per-launch events)";
+    if (c->world > 1 && c->opt_exchange != 1) return "ncclAllGather exchange";
+    if (gemv_variant(c->variant).ctas_per_sm != 1) return "variant runs 2 CTAs per SM";
+    const int pi = persist_index(c);
+    if (pi < 0) return "no persistent instantiation of this tile shape";
+    if (c->nchunks > (long long)persist_max_chunks() * c->nblk) return "N too large for the per-CTA vector chunks";
+    int qs_n, scr_n;
+    persist_scratch(c, &qs_n, &scr_n);
+    if (persist_variant(pi).smem_fixed() + (size_t)(qs_n + scr_n) * 8 + 256 > (size_t)c->smem_optin)
+        return "tile ring + scratch exceed shared memory";
+    return nullptr;
+}
+
+int launch_persist(cgb_ctx *c, long long iters)
+{
+    PersistArgs a;
+    memset(&a, 0, sizeof a);
+    a.A = c->A;
+    a.x = c->x;
+    a.r = c->r;
+    a.p = c->p;
+    a.rrpart = c->rrpart;
+    for (int g = 0; g < kMaxWorld; ++g) a.peer_ll[g] = c->peer_ll[g];
+    if (c->opt_loopback)
+        for (int g = 0; g < c->world; ++g) a.peer_ll[g] = c->ll + ((long long)g - c->rank) * c->slot;
+    a.ll = c->ll;
+    a.sync = c->psync;
+    a.st = c->st;
+    a.ctl = c->ctl;
+    a.hist = c->hist;
+    a.host_done = c->d_hdone;
+    a.ld = c->ld;
+    a.rows = c->rows;
+    a.row0 = c->row0;
+    a.n = c->n;
+    a.maxrows = c->maxrows;
+    a.n_loc = c->n_loc > 0 ? c->n_loc : 1;
+    a.slot = c->slot;
+    a.bufstride = c->bufstride;
+    a.slot_off = (long long)c->rank * c->slot;
+    a.nchunks = c->nchunks;
+    a.rank = c->rank;
+    a.world = c->world;
+    a.iters = (int)iters;
+    a.l2_prefetch = c->opt_l2_prefetch;
+    persist_scratch(c, &a.qs_n, &a.scr_n);
+    a.tol = c->tol;
+    a.spin_ns = (unsigned long long)c->spin_timeout_ms * 1000000ULL;
+    if (c->trace_cap > 0) a.trace = make_trace(c, 0, c->nblk);
+    CK(cudaMemsetAsync(c->psync, 0, sizeof(PersistSync), c->stream));
+    CK(persist_variant(persist_index(c)).launch(a, c->nblk, c->stream));
+    c->kernel_launches += 1;
+    c->persist_launches += 1;
+    return CGB_OK;
+}
+
 bool exchange_configured(const cgb_ctx *c)
 {
     return c->world == 1 || (c->opt_exchange == 1 ? c->p2p_ready : c->comm != nullptr);
@@ -421,6 +507,10 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
     c->world = world;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("CGB_SPIN_TIMEOUT_MS")) { // default of the option "spin_timeout_ms"
+        const long long v = atoll(e);
+        if (v >= 1 && v <= 3600000) c->spin_timeout_ms = v;
+    }
     std::vector<int64_t> start(world), num(world);
     cgb_partition(n, world, start.data(), num.data());
     c->row0 = start[rank];
@@ -459,12 +549,15 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
     c->bufstride = (long long)c->world * c->slot_cap;
     CKB(cudaMalloc(&c->apx, (size_t)c->bufstride * sizeof(double)));
     CKB(cudaMalloc(&c->ctl, sizeof(Ctl)));
-    if (world > 1) {
+    {   // LL gather buffers: the fused exchange (world > 1) and the persistent schedule (any world)
         c->ll_bytes = (size_t)2 * c->bufstride * sizeof(uint4);
         CKB(cudaMalloc(&c->ll, c->ll_bytes));
         CKB(cudaMemsetAsync(c->ll, 0, c->ll_bytes, c->stream)); // tag 0 is never used
         c->peer_ll[rank] = c->ll;
     }
+    CKB(cudaMalloc(&c->psync, sizeof(PersistSync)));
+    CKB(cudaMemsetAsync(c->psync, 0, sizeof(PersistSync), c->stream));
+    CKB(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CKB(cudaMemsetAsync(c->ctl, 0, sizeof(Ctl), c->stream));
     CKB(cudaMalloc(&c->rrpart, (size_t)c->nchunks * sizeof(double)));
     CKB(cudaMalloc(&c->scratch, (size_t)(3 * c->nchunks + 8) * sizeof(double)));
@@ -485,6 +578,7 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
     CKB(cudaStreamSynchronize(c->stream));
     CKB(preload_vec_kernels());
     CKB(gemv_variant(c->variant).preload());
+    if (persist_index(c) >= 0) CKB(persist_variant(persist_index(c)).preload());
 #undef CKB
     *out = c;
     return CGB_OK;
@@ -507,6 +601,7 @@ extern "C" int cgb_destroy(cgb_ctx *c)
     if (c->compat_part) cudaFree(c->compat_part);
     free_trace(c);
     if (c->ll) cudaFree(c->ll);
+    if (c->psync) cudaFree(c->psync);
     if (c->ctl) cudaFree(c->ctl);
     if (c->h_done) cudaFreeHost(c->h_done);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -749,14 +844,18 @@ extern "C" int cgb_set_rhs(cgb_ctx *c, const double *b_host)
 extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
 {
     if (!c || !key) return fail(CGB_ERR_INVALID, "null argument");
-    if (c->in_solve) return fail(CGB_ERR_STATE, "options cannot change during a solve");
     const std::string k(key);
+    // the schedules hand the complete state over between launches, so this one may change mid-solve
+    if (c->in_solve && k != "schedule") return fail(CGB_ERR_STATE, "options cannot change during a solve");
     if (k == "gemv_variant") {
         if (value < 0 || value >= gemv_variant_count())
             return fail(CGB_ERR_INVALID, "gemv_variant %lld out of range", (long long)value);
         set_variant(c, (int)value);
         drop_graph(c);
-        if (use_device(c) == CGB_OK) gemv_variant(c->variant).preload();
+        if (use_device(c) == CGB_OK) {
+            gemv_variant(c->variant).preload();
+            if (persist_index(c) >= 0) persist_variant(persist_index(c)).preload();
+        }
     } else if (k == "graph") {
         c->opt_graph = value != 0;
     } else if (k == "profile") {
@@ -796,6 +895,12 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
         if (value < 0 || value > 64) return fail(CGB_ERR_INVALID, "l2_prefetch must be in [0, 64] pipeline steps");
         c->opt_l2_prefetch = (int)value;
         drop_graph(c);
+    } else if (k == "schedule") {
+        if (value != 0 && value != 1) return fail(CGB_ERR_INVALID, "schedule must be 0 (graph of 3 kernels) or 1 (persistent)");
+        c->opt_schedule = (int)value;
+    } else if (k == "spin_timeout_ms") {
+        if (value < 1 || value > 3600000) return fail(CGB_ERR_INVALID, "spin_timeout_ms must be in [1, 3600000]");
+        c->spin_timeout_ms = value;
     } else if (k == "trace") {
         // keep %globaltimer timelines of the last `value` launches of the loop kernels (0 = off)
         if (value < 0 || value > 4096) return fail(CGB_ERR_INVALID, "trace must be in [0, 4096] launches");
@@ -875,6 +980,9 @@ extern "C" int cgb_get_option(cgb_ctx *c, const char *key, int64_t *value)
     else if (k == "l2_prefetch") *value = c->opt_l2_prefetch;
     else if (k == "exchange") *value = c->opt_exchange;
     else if (k == "trace") *value = c->trace_cap;
+    else if (k == "schedule") *value = c->opt_schedule;
+    else if (k == "schedule_in_use") *value = (c->opt_schedule == 1 && !persist_unusable(c)) ? 1 : 0;
+    else if (k == "spin_timeout_ms") *value = c->spin_timeout_ms;
     else if (k == "loopback") *value = c->opt_loopback;
     else if (k == "num_threads") *value = c->opt_num_threads;
     else if (k == "block_width") *value = c->opt_block_width;
@@ -963,6 +1071,32 @@ extern "C" int cgb_iterate(cgb_ctx *c, int64_t iters, float *ms)
     const bool profile = c->opt_profile != 0;
     const bool graph = c->opt_graph != 0 && !profile;
     const bool lockstep = c->world > 1 && c->opt_exchange == 0;
+    if (c->opt_schedule == 1 && !persist_unusable(c) && todo > 0) {
+        // ONE cooperative launch runs all `todo` loop bodies (it leaves the loop by itself on
+        // convergence): no graph, no per-iteration launch, no host polling
+        CK(cudaEventRecord(c->ev0, c->stream));
+        while (todo > 0) {
+            const long long part = std::min<long long>(todo, 1 << 30);
+            if ((rc = launch_persist(c, part))) return rc;
+            todo -= part;
+            c->launched += part;
+        }
+        CK(cudaEventRecord(c->ev1, c->stream));
+        cudaError_t e = cudaEventSynchronize(c->ev1);
+        if (e != cudaSuccess) {
+            const int code = *(volatile int *)c->h_done;
+            if (code < 0)
+                return fail(CGB_ERR_TIMEOUT, "a device-side wait (kind %d: 1 = peer rank's mat-vec rows, 2 = local "
+                            "mat-vec, 3 = r'r partials, 4 = p chunks) exceeded spin_timeout_ms = %lld: a rank is "
+                            "missing or stuck (%s)", -code, c->spin_timeout_ms, cudaGetErrorString(e));
+            CK(e);
+        }
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+        c->loop_ms += t;
+        if (ms) *ms = t;
+        return CGB_OK;
+    }
     if (graph && !c->graph_exec && todo >= c->graph_unroll) {
         if ((rc = build_graph(c))) return rc;
     }

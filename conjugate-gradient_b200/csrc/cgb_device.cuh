@@ -90,6 +90,31 @@ struct GemvArgs {
     Trace trace;          // diagnostic timeline (option "trace"); buf == nullptr: off
 };
 
+// ---- persistent schedule (persist.cu): the whole CG loop in one cooperative launch ----
+// Arrival counters of one launch (zeroed by the host before it): CTAs of THIS GPU that finished
+// their mat-vec rows, chunk partials of r'r published, chunks of p published.
+struct PersistSync {
+    unsigned int arrive_mv, arrive_rr, arrive_p, pad;
+};
+struct PersistArgs {
+    const double *A;           // rows x ld shard
+    double *x, *r, *p;         // full-length replicated vectors (ld doubles)
+    double *rrpart;            // nchunks chunk partials of r'r (also the hand-over to the next launch)
+    uint4 *peer_ll[kMaxWorld]; // every rank's LL gather buffers (self included)
+    const uint4 *ll;           // this rank's own LL buffers
+    PersistSync *sync;
+    State *st;
+    Ctl *ctl;
+    double *hist;              // nullable
+    int *host_done;            // mapped pinned flag: 1 = converged, < 0 = a wait timed out
+    long long ld, rows, row0, n, maxrows, n_loc, slot, bufstride, slot_off, nchunks;
+    int rank, world, iters, l2_prefetch;
+    int qs_n, scr_n;           // shared-memory scratch: rows per CTA, max(world * grid, nchunks)
+    double tol;
+    unsigned long long spin_ns; // bound of every cross-CTA / cross-rank wait
+    Trace trace;
+};
+
 // ------------------------------------------------------------------ reductions
 __device__ __forceinline__ double shfl_xor_f64(double v, int m)
 {
@@ -233,6 +258,12 @@ __device__ __forceinline__ void exchange_consumed(const Gather &g, int tid)
     }
 }
 
+__device__ __forceinline__ long long gather_index_raw(long long n_loc, int world, long long slot, long long i)
+{
+    long long r = i / n_loc;
+    if (r > world - 1) r = world - 1;
+    return r * slot + (i - r * n_loc);
+}
 __device__ __forceinline__ long long gather_index(const Gather &g, long long i)
 {
     long long r = i / g.n_loc;

@@ -43,6 +43,17 @@ const GemvVariant &gemv_variant(int i);
 cudaError_t launch_read_stream(const double *A, long long ndoubles, double *sink, int sm_count,
                                cudaStream_t s);
 
+// ---- persistent schedule (persist.cu): the CG loop as one cooperative launch --------------
+struct PersistVariant {
+    const char *name; // = the gemv.cu variant with the same tile shape
+    cudaError_t (*launch)(const PersistArgs &a, int nblk, cudaStream_t s);
+    cudaError_t (*preload)();
+    size_t (*smem_fixed)(); // shared memory without the size-dependent scratch (qs_n + scr_n doubles)
+};
+int persist_variant_count();
+const PersistVariant &persist_variant(int i);
+int persist_max_chunks(); // 256-element chunks of the vectors one CTA can own
+
 // ---- reference-topology mat-vec (compat.cu): NUM_THREADS / BLOCK_WIDTH honoured literally ----
 size_t compat_part_doubles(long long n, int block_width);
 cudaError_t launch_compat_matvec(const GemvArgs &a, int nblk, int num_threads, int block_width,

@@ -393,6 +393,7 @@ const GemvVariant kVariants[] = {
     {"ldg_w8r4u2", 4, 256, ldg_launch<8, 4, 2>, ldg_preload<8, 4, 2>},
     {"ldg_w8r2u4", 4, 256, ldg_launch<8, 2, 4>, ldg_preload<8, 2, 4>},
     {"ldg_w16r4u2", 2, 512, ldg_launch<16, 4, 2>, ldg_preload<16, 4, 2>},
+    {"tma_w4r1c2048s2", 1, 160, tma_launch<4, 1, 2048, 2, 1>, tma_preload<4, 1, 2048, 2, 1>},
 };
 
 } // namespace

@@ -1,0 +1,615 @@
+// persist.cu -- the whole CG loop (code/MPI/cg.cc:96-137) as ONE persistent cooperative kernel.
+//
+// The three-kernel schedule (gemv.cu + vec.cu, CUDA graph + programmatic dependent launch)
+// serialises, every iteration, mat-vec -> x/r update -> p update -> mat-vec through kernel
+// boundaries; its %globaltimer timeline (profiles/r02/trace_*) shows ~11 us of such chain plus
+// ~5 us of start skew per iteration on the 8-way shard (5000 x 40000, 230 us of streaming).
+// Here one CTA per SM stays resident for the whole solve; the iteration's three data
+// dependencies -- the reference's MPI_Allgatherv + 2 x MPI_Allreduce (cg.cc:105-136) -- become
+// data-flow waits inside the kernel, and the producer warp never stops streaming A:
+//
+//   phase M  mat-vec of this CTA's rows (the tile pipeline of gemv.cu, same summation order);
+//            every finished row and the CTA's p'Ap block partial go straight into EVERY rank's
+//            gather buffer as self-flagging LL entries (NVLink peer stores; also on 1 GPU).
+//   phase U  wait for all block partials of all ranks -> p'Ap, alpha; the CTA owns the
+//            256-element chunks c, c + grid, ... of the replicated vectors and keeps their
+//            x, r, p IN REGISTERS for the whole launch: x += alpha p, r -= alpha Ap (Ap polled
+//            from the LL entries), chunk partial of r'r -> rrpart[chunk], arrive on a counter.
+//   phase B  wait for all chunk partials -> r'r, stop test, beta; p = r + beta p for the own
+//            chunks, stored to the global p vector, arrive on a second counter.
+//   producer warp: meanwhile already has the A tiles of the next mat-vec in the shared-memory
+//            ring (A never changes) and more of them prefetched into L2; it waits for the p
+//            counter, then adds the p slices.  HBM keeps streaming across the iteration boundary.
+//
+// Every reduction has the order of oracle/cg_oracle.c (row dot, block partials in (rank, block)
+// order, chunk256 partials of the global vector, det_sum), so the result is bitwise equal to the
+// three-kernel schedule and to the CPU oracle.  All scalars are computed redundantly by every
+// CTA of every rank from identical data: no all-reduce, no host round trip, no launch per
+// iteration; the kernel leaves the loop by itself on sqrt(r'r) < tol (cg.cc:120-121).
+//
+// CTAs wait on one another, so the launch is cooperative (co-residency is guaranteed or the
+// launch fails).  Ranks on other GPUs are waited for through the LL entries they write, exactly
+// as in the fused exchange of the three-kernel schedule.
+#include "cgb_device.cuh"
+#include "cgb_kernels.h"
+
+namespace cgb {
+
+namespace {
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_add_u32(unsigned *p, unsigned v)
+{
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_cg_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_global()
+{
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+
+// A wait that can only end badly is reported before it faults the launch: the host finds the
+// code in the mapped flag and returns CGB_ERR_TIMEOUT instead of a bare "unspecified failure".
+__device__ __noinline__ void spin_timeout(const PersistArgs &a, int what)
+{
+    if (a.host_done) {
+        *a.host_done = -(what);
+        __threadfence_system();
+    }
+    __trap();
+}
+
+// Poll a counter another CTA of this GPU advances (one thread per CTA calls this).
+__device__ __forceinline__ void wait_counter(const PersistArgs &a, const unsigned *ctr, unsigned target, int what)
+{
+    if (ld_relaxed_u32(ctr) >= target) return;
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_relaxed_u32(ctr) < target) {
+        __nanosleep(32);
+        if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, what);
+    }
+}
+
+// One LL entry {lo, tag, hi, tag}: spin until both halves carry the tag.
+__device__ __forceinline__ double ll_wait(const PersistArgs &a, const uint4 *src, unsigned tag, uint4 v)
+{
+    if (v.y != tag || v.w != tag) {
+        const unsigned long long t0 = globaltimer_ns();
+        do {
+            __nanosleep(20);
+            v = ld_volatile_v4(src);
+            if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 1);
+        } while (v.y != tag || v.w != tag);
+    }
+    return __hiloint2double((int)v.z, (int)v.x);
+}
+
+// mbarrier wait with the configurable bound (a peer rank may legitimately be seconds late)
+__device__ __forceinline__ void mbar_wait_ns(const PersistArgs &a, uint64_t *bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = globaltimer_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 5);
+    }
+}
+
+} // namespace
+
+template <int CW, int RPW, int TC, int STAGES, int MAXC>
+__global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const PersistArgs a)
+{
+    constexpr int TR = CW * RPW;
+    constexpr int NCT = CW * 32;       // consumer threads
+    constexpr int EPT = kChunk / NCT;  // elements of a 256-chunk per consumer thread
+    static_assert(CW == 4 || CW == 8, "chunk256 mapping is written for 4 or 8 consumer warps");
+    static_assert(TC % 64 == 0, "tile width must be a multiple of 64 doubles");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sA = reinterpret_cast<double *>(smem_raw);            // [STAGES][TR][TC]
+    double *sP = sA + (size_t)STAGES * TR * TC;                   // [STAGES][TC]
+    uint64_t *full = reinterpret_cast<uint64_t *>(sP + (size_t)STAGES * TC);
+    uint64_t *empty = full + STAGES;
+    double *wsum = reinterpret_cast<double *>(empty + STAGES);    // [8]
+    double *s_sc = wsum + 8;                                      // [4] broadcast scalars
+    double *qs = s_sc + 4;                                        // [rows of this CTA]
+    double *scr = qs + a.qs_n;                                    // [max(world * grid, nchunks)]
+    __shared__ volatile int s_stop;                               // consumers -> producer: loop left
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nblk = gridDim.x, c = blockIdx.x;
+    const long long r0 = (long long)c * a.rows / nblk;
+    const long long r1 = (long long)(c + 1) * a.rows / nblk;
+    const int nrows = (int)(r1 - r0);
+    const int nb = (nrows + TR - 1) / TR;          // row blocks, balanced below
+    const int ntc = (int)((a.ld + TC - 1) / TC);   // column tiles
+    const unsigned T = (unsigned)nb * (unsigned)ntc; // pipeline steps per mat-vec
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CW);
+        }
+        fence_mbar_init();
+        s_stop = 0;
+    }
+    __syncthreads();
+    if (a.st->done) return; // converged in an earlier launch: nothing to do (uniform)
+
+    const unsigned nchunks = (unsigned)a.nchunks;
+
+    if (warp == CW) {
+        // ================= producer: streams A, never waits for the vector phases =================
+        if (T == 0) return;
+        const uint64_t pol_a = l2_policy_evict_first();
+        const uint64_t pol_p = l2_policy_evict_last();
+        // global step g -> (row block b, column tile t) of mat-vec g / T
+        auto geom = [&](unsigned g, long long &rb0, int &nr, long long &c0, int &w) {
+            const unsigned l = g % T;
+            const int b = (int)(l / (unsigned)ntc), t = (int)(l - (unsigned)b * (unsigned)ntc);
+            rb0 = r0 + (long long)b * nrows / nb;
+            nr = (int)(r0 + (long long)(b + 1) * nrows / nb - rb0);
+            c0 = (long long)t * TC;
+            w = (int)((a.ld - c0 < TC) ? (a.ld - c0) : TC);
+        };
+        auto issueA = [&](unsigned g) {
+            long long rb0, c0;
+            int nr, w;
+            geom(g, rb0, nr, c0, w);
+            const int stage = g % STAGES;
+            if (lane == 0) mbar_arrive_expect_tx(&full[stage], (unsigned)((nr + 1) * w * 8));
+            __syncwarp();
+            double *dstA = sA + (size_t)stage * TR * TC;
+            for (int j = lane; j < nr; j += 32)
+                bulk_g2s(dstA + (size_t)j * TC, a.A + (rb0 + j) * a.ld + c0, (unsigned)(w * 8), &full[stage], pol_a);
+        };
+        auto issueP = [&](unsigned g) {
+            long long rb0, c0;
+            int nr, w;
+            geom(g, rb0, nr, c0, w);
+            const int stage = g % STAGES;
+            if (lane == 0) bulk_g2s(sP + (size_t)stage * TC, a.p + c0, (unsigned)(w * 8), &full[stage], pol_p);
+        };
+        auto wait_empty = [&](unsigned g) {
+            if (g >= (unsigned)STAGES) mbar_wait_ns(a, &empty[g % STAGES], ((g / STAGES) & 1u) ^ 1u);
+        };
+        unsigned pre = 0; // steps of the coming mat-vec whose A part is already in flight
+        for (int m = 0; m < a.iters; ++m) {
+            const unsigned base = (unsigned)m * T;
+            if (m > 0) {
+                // p of this mat-vec is final once every chunk owner has published it -- or the
+                // loop was left (converged): then only the copies in flight must still land
+                int stop = 0;
+                if (lane == 0) {
+                    const unsigned target = nchunks * (unsigned)m;
+                    const unsigned long long t0 = globaltimer_ns();
+                    while (ld_relaxed_u32(&a.sync->arrive_p) < target) {
+                        if (s_stop) {
+                            stop = 1;
+                            break;
+                        }
+                        __nanosleep(32);
+                        if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 4);
+                    }
+                }
+                stop = __shfl_sync(0xffffffffu, stop, 0);
+                if (stop) {
+                    for (unsigned u = 0; u < pre; ++u) issueP(base + u);
+                    for (unsigned u = 0; u < pre; ++u) mbar_wait_ns(a, &full[(base + u) % STAGES], ((base + u) / STAGES) & 1u);
+                    return;
+                }
+                __threadfence();            // acquire: the chunk owners' stores to p ...
+                fence_proxy_async_global(); // ... are read below through the async proxy (TMA)
+            }
+            for (unsigned u = 0; u < pre; ++u) issueP(base + u);
+            for (unsigned g = base + pre; g < base + T; ++g) {
+                wait_empty(g);
+                issueA(g);
+                issueP(g);
+            }
+            pre = 0;
+            if (m + 1 < a.iters) {
+                // run ahead into the next mat-vec: A tiles into the ring as its stages drain, the
+                // steps after them into L2, while the vector phases of this iteration run
+                const unsigned npre = T < (unsigned)STAGES ? T : (unsigned)STAGES;
+                for (; pre < npre; ++pre) {
+                    wait_empty(base + T + pre);
+                    issueA(base + T + pre);
+                }
+                unsigned npf = pre + (unsigned)a.l2_prefetch;
+                if (npf > T) npf = T;
+                for (unsigned u = pre; u < npf; ++u) {
+                    long long rb0, c0;
+                    int nr, w;
+                    geom(base + T + u, rb0, nr, c0, w);
+                    for (int j = lane; j < nr; j += 32)
+                        bulk_prefetch_l2(a.A + (rb0 + j) * a.ld + c0, (unsigned)(w * 8));
+                }
+            }
+        }
+        return;
+    }
+
+    // ======================================= consumers =======================================
+    const long long it0 = a.st->iter;                       // loop bodies book-kept so far - 1 ...
+    const unsigned epoch0 = (unsigned)a.ctl->epoch;         // exchanges consumed so far
+    unsigned long long *const trace = a.trace.buf;
+    const unsigned tr0 = (trace && tid == 0) ? a.trace.cnt[c] : 0u; // iterations traced before this launch
+
+    // chunks of the replicated vectors this CTA owns: c, c + grid, ...; element el of a chunk
+    // belongs to consumer thread el % NCT (32-group el / 32 = warp + e * CW)
+    double xs[MAXC][EPT], rs[MAXC][EPT], ps[MAXC][EPT];
+    unsigned mychunks = 0;
+#pragma unroll
+    for (int cc = 0; cc < MAXC; ++cc) {
+        const long long j = (long long)c + (long long)cc * nblk;
+        if (j < a.nchunks) ++mychunks;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const long long i = j * kChunk + tid + e * NCT;
+            const bool ok = j < a.nchunks && i < a.n;
+            xs[cc][e] = ok ? a.x[i] : 0.0;
+            rs[cc][e] = ok ? a.r[i] : 0.0;
+            ps[cc][e] = ok ? a.p[i] : 0.0;
+        }
+    }
+    // deferred book-keeping of the previous loop body (advance_state of the 3-kernel schedule):
+    // rsold = r'r from the chunk partials the previous kernel left in rrpart
+    for (unsigned t = tid; t < nchunks; t += NCT) scr[t] = a.rrpart[t];
+    named_bar_sync(1, NCT);
+    if (warp == 0) {
+        const double s = warp_det_sum(scr, nchunks, lane);
+        if (lane == 0) {
+            s_sc[0] = s;
+            if (c == 0 && it0 >= 0 && a.hist) a.hist[it0] = s;
+        }
+    }
+    named_bar_sync(1, NCT);
+    double rsold = s_sc[0];
+    double rsnew = rsold, alpha = 0.0, conj = 0.0;
+    int converged = 0, executed = 0;
+
+    const uint4 *const own_ll = a.ll;
+    unsigned g = 0; // pipeline step counter, never reset (mbarrier parities)
+    for (int m = 0; m < a.iters; ++m) {
+        const long long jloop = it0 + 1 + m;             // the reference's k of this loop body
+        const unsigned tag = epoch0 + 1u + (unsigned)m;  // tag + buffer of this exchange
+        const long long lbase = (long long)(tag & 1u) * a.bufstride + a.slot_off;
+        const uint4 *const view = own_ll + (long long)(tag & 1u) * a.bufstride;
+        unsigned long long *rec = nullptr;
+        if (trace && tid == 0) {
+            rec = trace + ((size_t)((tr0 + (unsigned)m) % (unsigned)a.trace.cap) * (size_t)nblk + (size_t)c) * kTraceWords;
+            rec[0] = globaltimer_ns();
+            rec[7] = (unsigned long long)smid() | ((unsigned long long)nrows << 32);
+        }
+
+        // ------------------------------------------------ phase M: Ap rows of this CTA (cg.cc:100-102)
+        for (int b = 0; b < nb; ++b) {
+            const long long rb0 = r0 + (long long)b * nrows / nb;
+            const int nr = (int)(r0 + (long long)(b + 1) * nrows / nb - rb0);
+            const int nv = (nr > warp) ? ((nr - warp + CW - 1) / CW) : 0;
+            double acc0[RPW], acc1[RPW], prow[RPW];
+#pragma unroll
+            for (int s = 0; s < RPW; ++s) {
+                acc0[s] = 0.0;
+                acc1[s] = 0.0;
+                prow[s] = 0.0;
+            }
+            for (int t = 0; t < ntc; ++t, ++g) {
+                const int stage = g % STAGES;
+                const unsigned ph = (g / STAGES) & 1u;
+                const long long c0 = (long long)t * TC;
+                const int w = (int)((a.ld - c0 < TC) ? (a.ld - c0) : TC);
+                mbar_wait_ns(a, &full[stage], ph);
+                if (t == 0) {
+                    // the tile carries a p slice, so every chunk of p has been published:
+                    // p at this warp's own rows (for the p'Ap epilogue) is final too
+                    if (rec && b == 0) rec[3] = globaltimer_ns();
+#pragma unroll
+                    for (int s = 0; s < RPW; ++s)
+                        if (s < nv) prow[s] = ld_cg_f64(a.p + a.row0 + rb0 + warp + s * CW);
+                }
+                const double2 *sa2 = reinterpret_cast<const double2 *>(sA + (size_t)stage * TR * TC);
+                const double2 *sp2 = reinterpret_cast<const double2 *>(sP + (size_t)stage * TC);
+                if (nv == RPW && w == TC) {
+#pragma unroll
+                    for (int i = 0; i < TC / 64; ++i) {
+                        const int q = lane + 32 * i;
+                        const double2 pv = sp2[q];
+#pragma unroll
+                        for (int s = 0; s < RPW; ++s) {
+                            const double2 av = sa2[(warp + s * CW) * (TC / 2) + q];
+                            acc0[s] = __fma_rn(av.x, pv.x, acc0[s]);
+                            acc1[s] = __fma_rn(av.y, pv.y, acc1[s]);
+                        }
+                    }
+                } else {
+                    const int nq = w >> 1;
+                    for (int q = lane; q < nq; q += 32) {
+                        const double2 pv = sp2[q];
+#pragma unroll
+                        for (int s = 0; s < RPW; ++s) {
+                            if (s < nv) {
+                                const double2 av = sa2[(warp + s * CW) * (TC / 2) + q];
+                                acc0[s] = __fma_rn(av.x, pv.x, acc0[s]);
+                                acc1[s] = __fma_rn(av.y, pv.y, acc1[s]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+            }
+            // row epilogue: butterfly, Ap_row to every rank, p_row * Ap_row for the block partial
+#pragma unroll
+            for (int s = 0; s < RPW; ++s) {
+                if (s < nv) {
+                    const double y = warp_butterfly(__dadd_rn(acc0[s], acc1[s]));
+                    if (lane == 0) {
+                        const long long li = rb0 + warp + s * CW;
+#pragma unroll
+                        for (int gg = 0; gg < kMaxWorld; ++gg)
+                            if (gg < a.world) ll_store(a.peer_ll[gg] + lbase + li, y, tag);
+                        qs[li - r0] = __dmul_rn(prow[s], y);
+                    }
+                }
+            }
+        }
+        named_bar_sync(1, NCT);
+        if (warp == 0) {
+            const double bp = warp_det_sum(qs, nrows, lane); // level 1 of p'Ap (cg.cc:105)
+            if (lane == 0) {
+#pragma unroll
+                for (int gg = 0; gg < kMaxWorld; ++gg)
+                    if (gg < a.world) ll_store(a.peer_ll[gg] + lbase + a.maxrows + c, bp, tag);
+                red_add_u32(&a.sync->arrive_mv, 1u); // a hint for the local waiters, not a flag
+                if (rec) rec[5] = globaltimer_ns();
+                // cheap gate before anybody polls LL entries: all CTAs of THIS GPU are through
+                wait_counter(a, &a.sync->arrive_mv, (unsigned)nblk * (unsigned)(m + 1), 2);
+            }
+        }
+        named_bar_sync(1, NCT);
+
+        // ------------------------------------------------ phase U: alpha, x, r, r'r partials (cg.cc:105-116)
+        {
+            const int total = a.world * nblk;
+            for (int t0 = tid; t0 < total; t0 += 4 * NCT) {
+                uint4 v[4];
+                const uint4 *src[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + u * NCT;
+                    const int rk = t / nblk, cb = t - rk * nblk;
+                    src[u] = view + (long long)rk * a.slot + a.maxrows + cb;
+                    if (t < total) v[u] = ld_volatile_v4(src[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = t0 + u * NCT;
+                    if (t < total) scr[t] = ll_wait(a, src[u], tag, v[u]);
+                }
+            }
+            named_bar_sync(1, NCT);
+            if (warp == 0) {
+                const double cj = warp_det_sum(scr, total, lane);                 // p'Ap, every rank's blocks
+                const double clamp = __dmul_rn(rsold, kNearZero);
+                const double al = __ddiv_rn(rsold, (cj < clamp) ? clamp : cj);    // cg.cc:107
+                if (lane == 0) {
+                    s_sc[1] = al;
+                    s_sc[3] = cj;
+                }
+            }
+            named_bar_sync(1, NCT);
+            alpha = s_sc[1];
+            conj = s_sc[3];
+            if (rec) rec[1] = globaltimer_ns();
+        }
+#pragma unroll
+        for (int cc = 0; cc < MAXC; ++cc) {
+            const long long j = (long long)c + (long long)cc * nblk;
+            if (j < a.nchunks) { // uniform over the CTA
+                double v = 0.0;
+                uint4 e4[EPT];
+                const uint4 *esrc[EPT];
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const long long i = j * kChunk + tid + e * NCT;
+                    esrc[e] = view + gather_index_raw(a.n_loc, a.world, a.slot, i < a.n ? i : 0);
+                    if (i < a.n) e4[e] = ld_volatile_v4(esrc[e]);
+                }
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const long long i = j * kChunk + tid + e * NCT;
+                    double sq = 0.0;
+                    if (i < a.n) {
+                        const double ap = ll_wait(a, esrc[e], tag, e4[e]);
+                        xs[cc][e] = __fma_rn(alpha, ps[cc][e], xs[cc][e]);   // cg.cc:110
+                        rs[cc][e] = __fma_rn(-alpha, ap, rs[cc][e]);        // cg.cc:113
+                        sq = __dmul_rn(rs[cc][e], rs[cc][e]);               // cg.cc:116
+                    }
+                    const double bf = warp_butterfly(sq);                   // 32-group warp + e * CW
+                    v = (e == 0) ? bf : __dadd_rn(v, bf);                   // group g + group g + 4
+                }
+                // chunk256: the remaining levels of the perfect tree, across the consumer warps
+                if (lane == 0) wsum[warp] = v;
+                named_bar_sync(1, NCT);
+                if (warp == 0) {
+                    double t = (lane < CW) ? wsum[lane] : 0.0;
+                    if (CW == 8) t = __dadd_rn(t, shfl_xor_f64(t, 4));
+                    t = __dadd_rn(t, shfl_xor_f64(t, 2));
+                    t = __dadd_rn(t, shfl_xor_f64(t, 1));
+                    if (lane == 0) a.rrpart[j] = t;
+                }
+                named_bar_sync(1, NCT);
+            }
+        }
+        if (tid == 0) {
+            if (mychunks) {
+                __threadfence(); // release rrpart[own chunks]
+                red_add_u32(&a.sync->arrive_rr, mychunks);
+            }
+            if (rec) rec[2] = globaltimer_ns();
+            // ------------------------------------------------ phase B: r'r, stop test, beta (cg.cc:116-124)
+            wait_counter(a, &a.sync->arrive_rr, nchunks * (unsigned)(m + 1), 3);
+            __threadfence(); // acquire
+        }
+        named_bar_sync(1, NCT);
+        for (unsigned t = tid; t < nchunks; t += NCT) scr[t] = ld_cg_f64(a.rrpart + t);
+        named_bar_sync(1, NCT);
+        if (warp == 0) {
+            const double s = warp_det_sum(scr, nchunks, lane);
+            if (lane == 0) s_sc[2] = s;
+        }
+        named_bar_sync(1, NCT);
+        rsnew = s_sc[2];
+        executed = m + 1;
+        if (rec) rec[4] = globaltimer_ns();
+        if (c == 0 && tid == 0 && a.hist) a.hist[jloop] = rsnew;
+        if (sqrt(rsnew) < a.tol) { // cg.cc:120-121: leave BEFORE p and rsold are updated
+            converged = 1;
+            if (tid == 0) s_stop = 1;
+            break;
+        }
+        const double beta = __ddiv_rn(rsnew, rsold); // cg.cc:124
+        rsold = rsnew;                               // cg.cc:132
+#pragma unroll
+        for (int cc = 0; cc < MAXC; ++cc) {
+            const long long j = (long long)c + (long long)cc * nblk;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const long long i = j * kChunk + tid + e * NCT;
+                if (j < a.nchunks && i < a.n) {
+                    ps[cc][e] = __fma_rn(beta, ps[cc][e], rs[cc][e]); // cg.cc:127-129
+                    a.p[i] = ps[cc][e];
+                }
+            }
+        }
+        named_bar_sync(1, NCT);
+        if (tid == 0) {
+            if (mychunks) {
+                __threadfence(); // release p[own chunks] to every CTA's producer
+                red_add_u32(&a.sync->arrive_p, mychunks);
+            }
+            if (rec) rec[6] = globaltimer_ns();
+        }
+    }
+
+    // ---- hand the state back: x, r of the own chunks (p is already in place), scalars by CTA 0
+#pragma unroll
+    for (int cc = 0; cc < MAXC; ++cc) {
+        const long long j = (long long)c + (long long)cc * nblk;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+            const long long i = j * kChunk + tid + e * NCT;
+            if (j < a.nchunks && i < a.n) {
+                a.x[i] = xs[cc][e];
+                a.r[i] = rs[cc][e];
+            }
+        }
+    }
+    if (trace && tid == 0) a.trace.cnt[c] += (unsigned)executed;
+    if (c == 0 && tid == 0) {
+        State *st = a.st;
+        st->conj = conj;
+        st->alpha = alpha;
+        st->rsnew = rsnew;
+        if (converged) {
+            // the reference prints the STALE rsold and k = loop index at the break
+            st->rsold = rsold;
+            st->iter = it0 + executed;
+            st->done = 1;
+            if (a.host_done) *a.host_done = 1;
+            __threadfence_system();
+        } else {
+            // "inside loop body it0 + executed": rrpart holds its r'r partials; the next launch
+            // (or cgb_solve_end) does the deferred rsold = rsnew / iter + 1, as in vec.cu
+            st->rsold = rsold;
+            st->iter = it0 + executed;
+        }
+        a.ctl->epoch = a.ctl->epoch + (unsigned long long)executed;
+    }
+}
+
+// --------------------------------------------------------------------------------- host side
+namespace {
+
+template <int CW, int RPW, int TC, int STAGES>
+size_t persist_smem(const PersistArgs &a)
+{
+    return (size_t)STAGES * CW * RPW * TC * 8 + (size_t)STAGES * TC * 8 + 2 * STAGES * 8 + (8 + 4) * 8 +
+           ((size_t)a.qs_n + (size_t)a.scr_n) * 8;
+}
+
+constexpr int kPersistMaxChunks = 4; // 256-chunks of the vectors per CTA (N <= 4 * 148 * 256)
+
+template <int CW, int RPW, int TC, int STAGES>
+cudaError_t persist_launch(const PersistArgs &a, int nblk, cudaStream_t s)
+{
+    auto k = cg_persist_kernel<CW, RPW, TC, STAGES, kPersistMaxChunks>;
+    const size_t smem = persist_smem<CW, RPW, TC, STAGES>(a);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)nblk, 1, 1);
+    cfg.blockDim = dim3((unsigned)((CW + 1) * 32), 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; // CTAs wait on one another: co-residency or failure
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, a);
+}
+
+template <int CW, int RPW, int TC, int STAGES>
+size_t persist_smem_fixed()
+{
+    PersistArgs z;
+    memset(&z, 0, sizeof z);
+    return persist_smem<CW, RPW, TC, STAGES>(z);
+}
+
+template <int CW, int RPW, int TC, int STAGES>
+cudaError_t persist_preload()
+{
+    cudaFuncAttributes fa;
+    return cudaFuncGetAttributes(&fa, cg_persist_kernel<CW, RPW, TC, STAGES, kPersistMaxChunks>);
+}
+
+const PersistVariant kPersist[] = {
+    // the tile shapes of the gemv.cu variants of the same name (1 CTA per SM, 4 or 8 consumer warps)
+    {"tma_w8r2c512s3", persist_launch<8, 2, 512, 3>, persist_preload<8, 2, 512, 3>, persist_smem_fixed<8, 2, 512, 3>},
+    {"tma_w8r1c512s6", persist_launch<8, 1, 512, 6>, persist_preload<8, 1, 512, 6>, persist_smem_fixed<8, 1, 512, 6>},
+    {"tma_w4r4c512s3", persist_launch<4, 4, 512, 3>, persist_preload<4, 4, 512, 3>, persist_smem_fixed<4, 4, 512, 3>},
+    {"tma_w8r2c256s6", persist_launch<8, 2, 256, 6>, persist_preload<8, 2, 256, 6>, persist_smem_fixed<8, 2, 256, 6>},
+    {"tma_w8r1c1024s3", persist_launch<8, 1, 1024, 3>, persist_preload<8, 1, 1024, 3>, persist_smem_fixed<8, 1, 1024, 3>},
+    {"tma_w4r2c1024s3", persist_launch<4, 2, 1024, 3>, persist_preload<4, 2, 1024, 3>, persist_smem_fixed<4, 2, 1024, 3>},
+    {"tma_w4r1c2048s2", persist_launch<4, 1, 2048, 2>, persist_preload<4, 1, 2048, 2>, persist_smem_fixed<4, 1, 2048, 2>},
+};
+
+} // namespace
+
+int persist_variant_count() { return (int)(sizeof(kPersist) / sizeof(kPersist[0])); }
+const PersistVariant &persist_variant(int i) { return kPersist[i]; }
+int persist_max_chunks() { return kPersistMaxChunks; }
+
+} // namespace cgb

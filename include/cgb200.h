@@ -35,7 +35,8 @@ typedef enum cgb_status {
     CGB_ERR_NO_DEVICE = 3, /* no CUDA device / driver */
     CGB_ERR_CUDA = 4,      /* a CUDA runtime call failed */
     CGB_ERR_NCCL = 5,      /* NCCL missing or a NCCL call failed */
-    CGB_ERR_NOMEM = 6
+    CGB_ERR_NOMEM = 6,
+    CGB_ERR_TIMEOUT = 7    /* a device-side wait on another rank exceeded "spin_timeout_ms" */
 } cgb_status;
 
 typedef struct cgb_ctx cgb_ctx;
@@ -115,6 +116,14 @@ int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
  * mat-vec prefetches A while the vector updates still run); "l2_prefetch": pipeline steps of A
  * the mat-vec additionally pulls into L2 before that wait (0 = off);
  * "exchange": 0 ncclAllGather / 1 fused peer stores (see cgb_exchange_import);
+ * "schedule": 1 (default) = the whole loop of cgb_iterate as ONE persistent cooperative kernel
+ * (one CTA per SM stays resident, the iteration's dependencies are data-flow waits inside the
+ * kernel, A streams across iteration boundaries), 0 = a CUDA graph of three kernels per
+ * iteration; bitwise identical results; "schedule_in_use" (read-only) tells which one the
+ * current configuration gets (the persistent kernel needs the fused exchange, a 1-CTA-per-SM
+ * variant, and is not used with "compat" / "profile");
+ * "spin_timeout_ms": bound of the device-side waits on other ranks (default 20000); when it
+ * expires the call returns CGB_ERR_TIMEOUT (the context is then unusable);
  * "trace": launches kept by the diagnostic timeline (cgb_trace_read; 0 = off);
  * "loopback": profiling aid -- a rank of world > 1 with no peers aims every peer pointer of the
  * fused exchange at its own buffer, so ONE GPU runs one rank's shard under the production

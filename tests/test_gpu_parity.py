@@ -118,11 +118,16 @@ def test_dot_bitwise(cgb, O, n):
 
 
 # --------------------------------------------------------------------------- solve
-def _solve_gpu(cgb, n, setup, max_iter, variant=None, graph=1, x0=None):
+SCHEDULES = {"persistent": (1, 1), "graph": (0, 1), "launches": (0, 0)}   # (schedule, graph)
+
+
+def _solve_gpu(cgb, n, setup, max_iter, variant=None, graph=1, x0=None, schedule=None):
     with _ctx(cgb, n) as ctx:
         if variant is not None:
             ctx.set_option("gemv_variant", variant)
         ctx.set_option("graph", graph)
+        if schedule is not None:
+            ctx.set_option("schedule", schedule)
         setup(ctx)
         x = np.zeros(n) if x0 is None else x0.copy()
         info, hist = ctx.solve(x, max_iter=max_iter, tol=1e-10, history=True)
@@ -132,16 +137,19 @@ def _solve_gpu(cgb, n, setup, max_iter, variant=None, graph=1, x0=None):
 
 
 @pytest.mark.parametrize("n,max_iter", [(1000, 50), (1024, 1024), (1448, 200), (2048, 2048)])
-@pytest.mark.parametrize("graph", [0, 1])
-def test_solve_generated_bitwise_vs_oracle(cgb, O, n, max_iter, graph):
-    """Whole solve == oracle bit for bit: iteration count, every r'r, final x, DEBUG numbers."""
+@pytest.mark.parametrize("sched", list(SCHEDULES))
+def test_solve_generated_bitwise_vs_oracle(cgb, O, n, max_iter, sched):
+    """Whole solve == oracle bit for bit: iteration count, every r'r, final x, DEBUG numbers --
+    under every schedule of the loop: ONE persistent cooperative kernel (csrc/persist.cu, the
+    default), a CUDA graph of three kernels per iteration, plain launches."""
     b = O.init_source_term(n)
 
     def setup(ctx):
         ctx.generate_lap2d()
         ctx.set_rhs(b)
 
-    x, info, hist, nx, rr, nblk = _solve_gpu(cgb, n, setup, max_iter, graph=graph)
+    schedule, graph = SCHEDULES[sched]
+    x, info, hist, nx, rr, nblk = _solve_gpu(cgb, n, setup, max_iter, graph=graph, schedule=schedule)
     ref = O.solve(O.generate_lap2d(n), b, max_iter=max_iter, nranks=1, nblk=nblk)
     assert info.k == ref.k and bool(info.converged) == ref.converged
     assert info.iterations == len(ref.hist)
@@ -168,6 +176,61 @@ def test_solve_nonzero_x0_and_variants(cgb, O):
         assert info.k == ref.k, name
         assert np.array_equal(hist, ref.hist), name
         assert np.array_equal(x, ref.x), name
+
+
+def _persist_variants(cgb, n):
+    """Variants for which the persistent kernel is instantiated (option "schedule_in_use")."""
+    out = []
+    with _ctx(cgb, n) as ctx:
+        for v, name in enumerate(cgb.gemv_variants()):
+            ctx.set_option("gemv_variant", v)
+            if ctx.get_option("schedule_in_use") == 1:
+                out.append((v, name))
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 2, 17, 255, 257, 1001, 4097])
+def test_persistent_schedule_ragged_sizes_every_shape(cgb, O, n):
+    """The persistent kernel on ragged sizes (CTAs without rows, a last chunk of 1 element,
+    tiles narrower than the tile width), every instantiated tile shape, against the oracle."""
+    b = O.init_source_term(n)
+    A = O.generate_lap2d(n)
+    max_iter = min(n, 90)
+    variants = _persist_variants(cgb, n)
+    assert len(variants) >= 4, variants
+    ref = None
+    for v, name in variants:
+        def setup(ctx):
+            ctx.generate_lap2d()
+            ctx.set_rhs(b)
+        x, info, hist, nx, rr, nblk = _solve_gpu(cgb, n, setup, max_iter, variant=v, schedule=1)
+        if ref is None:
+            ref = O.solve(A, b, max_iter=max_iter, nranks=1, nblk=nblk)
+        assert info.k == ref.k and bool(info.converged) == ref.converged, name
+        assert np.array_equal(hist, ref.hist), name
+        assert np.array_equal(x, ref.x), name
+        assert nx == ref.norm_x and rr == ref.rel_resid, name
+
+
+def test_schedules_interleave_bitwise(cgb, O):
+    """cgb_iterate in pieces, alternating the persistent kernel and the three-kernel graph on the
+    same solve: the state handed over between launches (x, r, p, r'r partials, k) is complete,
+    so any split gives the bits of one uninterrupted solve."""
+    n = 3000
+    b = O.init_source_term(n)
+    with _ctx(cgb, n) as ctx:
+        ctx.generate_lap2d()
+        ctx.set_rhs(b)
+        nblk = ctx.layout().nblk
+        ctx.solve_begin(np.zeros(n), 150, 1e-10, True)
+        for sched, iters in ((1, 7), (0, 20), (1, 1), (1, 40), (0, 3), (1, 79)):
+            ctx.set_option("schedule", sched)
+            ctx.iterate(iters)
+        x, hist = np.zeros(n), np.zeros(150)
+        info = ctx.solve_end(x, hist)
+    ref = O.solve(O.generate_lap2d(n), b, max_iter=150, nranks=1, nblk=nblk)
+    assert info.k == ref.k == 150 and info.iterations == 150
+    assert np.array_equal(hist, ref.hist) and np.array_equal(x, ref.x)
 
 
 def test_solve_mtx_bitwise_vs_oracle(cgb, O, tmp_path):
