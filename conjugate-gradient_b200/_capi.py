@@ -60,6 +60,7 @@ SIGNATURES = [
     ("cgb_get_option", C.c_int, [_CTX, C.c_char_p, _i64p]),
     ("cgb_gemv_variant_count", C.c_int, []),
     ("cgb_gemv_variant_name", C.c_char_p, [C.c_int]),
+    ("cgb_autotune", C.c_int, [_CTX, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     ("cgb_get_layout", C.c_int, [_CTX, C.POINTER(Layout)]),
     ("cgb_solve", C.c_int, [_CTX, _dp, C.c_int64, C.c_double, _dp, C.POINTER(SolveInfo)]),
     ("cgb_solve_begin", C.c_int, [_CTX, _dp, C.c_int64, C.c_double, C.c_int]),
@@ -193,6 +194,15 @@ class Context:
         v = C.c_int64()
         _check(self._lib.cgb_get_option(self._h, key.encode(), C.byref(v)))
         return v.value
+
+    def autotune(self, iters: int = 0) -> dict:
+        """One-off tile-shape selection (cgb_autotune); returns the choice and every candidate's time."""
+        names = gemv_variants()
+        chosen = C.c_int(-1)
+        us = (C.c_float * len(names))()
+        _check(self._lib.cgb_autotune(self._h, iters, C.byref(chosen), us))
+        return {"chosen": names[chosen.value],
+                "us_per_iteration": {nm: round(float(t), 2) for nm, t in zip(names, us) if t >= 0}}
 
     # -- inputs
     def generate_lap2d(self):

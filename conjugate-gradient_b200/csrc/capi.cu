@@ -117,9 +117,11 @@ struct cgb_ctx {
     double *compat_part = nullptr; // chunk partials of the compat mat-vec
     size_t compat_part_cap = 0;
     int poll_every = 16, graph_unroll = 16, opt_pdl = 1, opt_l2_prefetch = 4;
+    int opt_l2_prefetch_mode = 0;  // persistent kernel: 0 = bulk prefetch (TMA), 1 = prefetch.global.L2 lines
     int opt_schedule = 1;          // 1: persistent cooperative kernel (persist.cu) when usable, 0: graph of 3 kernels
     long long spin_timeout_ms = 20000; // bound of the device-side waits on other CTAs / ranks
     PersistSync *psync = nullptr;
+    uint4 *rr_ll = nullptr;        // [2][nchunks] LL entries of the r'r chunk partials
     int smem_optin = 0;            // cudaDevAttrMaxSharedMemoryPerBlockOptin
     long long persist_launches = 0;
     int opt_loopback = 0;          // profiling: this rank plays every rank of the exchange (see "loopback")
@@ -389,6 +391,8 @@ int launch_persist(cgb_ctx *c, long long iters)
     if (c->opt_loopback)
         for (int g = 0; g < c->world; ++g) a.peer_ll[g] = c->ll + ((long long)g - c->rank) * c->slot;
     a.ll = c->ll;
+    a.rr_ll = c->rr_ll;
+    a.rr_stride = c->nchunks;
     a.sync = c->psync;
     a.st = c->st;
     a.ctl = c->ctl;
@@ -408,6 +412,7 @@ int launch_persist(cgb_ctx *c, long long iters)
     a.world = c->world;
     a.iters = (int)iters;
     a.l2_prefetch = c->opt_l2_prefetch;
+    a.l2_prefetch_mode = c->opt_l2_prefetch_mode;
     persist_scratch(c, &a.qs_n, &a.scr_n);
     a.tol = c->tol;
     a.spin_ns = (unsigned long long)c->spin_timeout_ms * 1000000ULL;
@@ -555,6 +560,8 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
         CKB(cudaMemsetAsync(c->ll, 0, c->ll_bytes, c->stream)); // tag 0 is never used
         c->peer_ll[rank] = c->ll;
     }
+    CKB(cudaMalloc(&c->rr_ll, (size_t)2 * c->nchunks * sizeof(uint4)));
+    CKB(cudaMemsetAsync(c->rr_ll, 0, (size_t)2 * c->nchunks * sizeof(uint4), c->stream));
     CKB(cudaMalloc(&c->psync, sizeof(PersistSync)));
     CKB(cudaMemsetAsync(c->psync, 0, sizeof(PersistSync), c->stream));
     CKB(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -602,6 +609,7 @@ extern "C" int cgb_destroy(cgb_ctx *c)
     free_trace(c);
     if (c->ll) cudaFree(c->ll);
     if (c->psync) cudaFree(c->psync);
+    if (c->rr_ll) cudaFree(c->rr_ll);
     if (c->ctl) cudaFree(c->ctl);
     if (c->h_done) cudaFreeHost(c->h_done);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -895,6 +903,8 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
         if (value < 0 || value > 64) return fail(CGB_ERR_INVALID, "l2_prefetch must be in [0, 64] pipeline steps");
         c->opt_l2_prefetch = (int)value;
         drop_graph(c);
+    } else if (k == "l2_prefetch_mode") {
+        c->opt_l2_prefetch_mode = value != 0;
     } else if (k == "schedule") {
         if (value != 0 && value != 1) return fail(CGB_ERR_INVALID, "schedule must be 0 (graph of 3 kernels) or 1 (persistent)");
         c->opt_schedule = (int)value;
@@ -981,6 +991,7 @@ extern "C" int cgb_get_option(cgb_ctx *c, const char *key, int64_t *value)
     else if (k == "exchange") *value = c->opt_exchange;
     else if (k == "trace") *value = c->trace_cap;
     else if (k == "schedule") *value = c->opt_schedule;
+    else if (k == "l2_prefetch_mode") *value = c->opt_l2_prefetch_mode;
     else if (k == "schedule_in_use") *value = (c->opt_schedule == 1 && !persist_unusable(c)) ? 1 : 0;
     else if (k == "spin_timeout_ms") *value = c->spin_timeout_ms;
     else if (k == "loopback") *value = c->opt_loopback;
@@ -1359,5 +1370,94 @@ extern "C" int cgb_trace_read(cgb_ctx *c, int which, uint64_t *out, int64_t capa
     CK(cudaMemcpy(&seen, c->trace_cnt[which], sizeof seen, cudaMemcpyDeviceToHost));
     if (launches) *launches = seen;
     if (blocks) *blocks = nb;
+    return CGB_OK;
+}
+
+// One-off selection of the mat-vec tile shape for THIS shard shape on THIS GPU (outside any timed
+// region): every candidate runs a few loop bodies of the schedule in use on the resident matrix,
+// the fastest is kept.  Box-to-box and shape-to-shape the best shape moves by several percent
+// (profiles/r02/tune_*), a static table does not hold.  Ranks of a world > 1 tune alone, with the
+// exchange looped back to themselves, so no peer has to take part; all tile shapes share one
+// summation order, so the choice never changes a result bit.
+extern "C" int cgb_autotune(cgb_ctx *c, int iters, int *chosen, float *us_per_iter)
+{
+    int rc = use_device(c);
+    if (rc) return rc;
+    if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
+    if (!c->matrix_set) return fail(CGB_ERR_STATE, "matrix not set");
+    if (iters < 1) iters = 12;
+    const int nv = gemv_variant_count();
+    if (us_per_iter)
+        for (int v = 0; v < nv; ++v) us_per_iter[v] = -1.f;
+    const int keep_variant = c->variant, keep_loopback = c->opt_loopback, keep_exchange = c->opt_exchange;
+    const bool keep_ready = c->p2p_ready;
+    const double keep_tol = c->tol;
+    const bool want_persist = c->opt_schedule == 1 && !c->opt_compat && !(c->world > 1 && keep_exchange == 0 && c->comm);
+    Ctl ctl0;
+    CK(cudaMemcpy(&ctl0, c->ctl, sizeof ctl0, cudaMemcpyDeviceToHost));
+    if (c->world > 1) { // tune alone: every peer pointer aims at the own buffer
+        c->opt_loopback = 1;
+        c->p2p_ready = true;
+        c->opt_exchange = 1;
+    }
+    c->tol = 0.0; // never converges
+    drop_graph(c);
+    int best = keep_variant;
+    float best_us = -1.f, default_us = -1.f;
+    for (int v = 0; v < nv && rc == CGB_OK; ++v) {
+        if (gemv_variant(v).ctas_per_sm != gemv_variant(keep_variant).ctas_per_sm) continue; // the grid (nblk) is part of the result's definition
+        if (strncmp(gemv_variant(v).name, "tma", 3) != 0 || strstr(gemv_variant(v).name, "nohint")) continue;
+        set_variant(c, v);
+        const bool persist = want_persist && !persist_unusable(c);
+        if (want_persist && !persist) continue; // compare like with like
+        if (gemv_variant(v).preload() != cudaSuccess) { cudaGetLastError(); continue; }
+        if (persist && persist_variant(persist_index(c)).preload() != cudaSuccess) { cudaGetLastError(); continue; }
+        float t_best = -1.f;
+        for (int rep = 0; rep < 3 && rc == CGB_OK; ++rep) { // rep 0 warms up
+            State s0;
+            memset(&s0, 0, sizeof s0);
+            s0.iter = -1;
+            CK(cudaMemcpyAsync(c->st, &s0, sizeof s0, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaEventRecord(c->ev0, c->stream));
+            if (persist) {
+                rc = launch_persist(c, iters);
+            } else {
+                for (int i = 0; i < iters && rc == CGB_OK; ++i) rc = launch_iteration(c);
+            }
+            if (rc) break;
+            CK(cudaEventRecord(c->ev1, c->stream));
+            CK(cudaEventSynchronize(c->ev1));
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+            if (rep > 0 && (t_best < 0.f || t < t_best)) t_best = t;
+        }
+        if (rc) break;
+        const float us = t_best * 1e3f / (float)iters;
+        if (us_per_iter) us_per_iter[v] = us;
+        if (v == keep_variant) default_us = us;
+        if (best_us < 0.f || us < best_us) {
+            best_us = us;
+            best = v;
+        }
+    }
+    // a candidate must beat the configured shape by more than the run-to-run noise
+    if (default_us > 0.f && best_us > default_us * 0.997f) best = keep_variant;
+    // leave no trace: state, exchange epoch and the LL entries written by the looped-back runs
+    c->opt_loopback = keep_loopback;
+    c->p2p_ready = keep_ready;
+    c->opt_exchange = keep_exchange;
+    c->tol = keep_tol;
+    set_variant(c, best);
+    drop_graph(c);
+    if (rc) return rc;
+    gemv_variant(best).preload();
+    if (persist_index(c) >= 0) persist_variant(persist_index(c)).preload();
+    CK(cudaMemcpyAsync(c->ctl, &ctl0, sizeof ctl0, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->ll, 0, c->ll_bytes, c->stream));
+    CK(cudaMemsetAsync(c->rr_ll, 0, (size_t)2 * c->nchunks * sizeof(uint4), c->stream));
+    CK(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
+    *c->h_done = 0;
+    CK(cudaStreamSynchronize(c->stream));
+    if (chosen) *chosen = best;
     return CGB_OK;
 }

@@ -102,13 +102,15 @@ struct PersistArgs {
     double *rrpart;            // nchunks chunk partials of r'r (also the hand-over to the next launch)
     uint4 *peer_ll[kMaxWorld]; // every rank's LL gather buffers (self included)
     const uint4 *ll;           // this rank's own LL buffers
+    uint4 *rr_ll;              // [2][rr_stride] LL entries: chunk partials of r'r (local to this GPU)
+    long long rr_stride;
     PersistSync *sync;
     State *st;
     Ctl *ctl;
     double *hist;              // nullable
     int *host_done;            // mapped pinned flag: 1 = converged, < 0 = a wait timed out
     long long ld, rows, row0, n, maxrows, n_loc, slot, bufstride, slot_off, nchunks;
-    int rank, world, iters, l2_prefetch;
+    int rank, world, iters, l2_prefetch, l2_prefetch_mode;
     int qs_n, scr_n;           // shared-memory scratch: rows per CTA, max(world * grid, nchunks)
     double tol;
     unsigned long long spin_ns; // bound of every cross-CTA / cross-rank wait

@@ -28,15 +28,16 @@ namespace cgb {
 // One result (a row of Ap, or the block partial of p'Ap) into the gather buffer: locally, or --
 // fused exchange -- as a self-flagging LL entry straight into every rank's buffer over NVLink
 // (peer stores).  That store IS the all-gather: no fence, no flag, no collective kernel.
+// Called by ALL lanes of a warp with the same value: in fused mode lane g stores to rank g -- one
+// store instruction with `world` transactions in flight (a loop in one lane serialises the
+// strong.sys stores: ~0.35 us each on the local GPU, a NVLink round trip each to a peer).
 __device__ __forceinline__ void store_out(const GemvArgs &a, long long plain_off, long long ll_off,
-                                          unsigned tag, double v)
+                                          unsigned tag, double v, int lane)
 {
     if (!a.p2p) {
-        a.base[plain_off] = v;
-    } else {
-#pragma unroll
-        for (int g = 0; g < kMaxWorld; ++g)
-            if (g < a.world) ll_store(a.peer_ll[g] + ll_off, v, tag);
+        if (lane == 0) a.base[plain_off] = v;
+    } else if (lane < a.world) {
+        ll_store(a.peer_ll[lane] + ll_off, v, tag);
     }
 }
 
@@ -207,12 +208,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
 #pragma unroll
             for (int s = 0; s < RPW; ++s) {
                 if (s < nv) {
-                    const double y = warp_butterfly(__dadd_rn(acc0[s], acc1[s]));
-                    if (lane == 0) {
-                        const long long li = rb0 + warp + s * CW;
-                        store_out(a, obase + li, lbase + li, tag, y);
-                        qs[li - r0] = __dmul_rn(prow[s], y);
-                    }
+                    const double y = warp_butterfly(__dadd_rn(acc0[s], acc1[s])); // in every lane
+                    const long long li = rb0 + warp + s * CW;
+                    store_out(a, obase + li, lbase + li, tag, y, lane);
+                    if (lane == 0) qs[li - r0] = __dmul_rn(prow[s], y);
                 }
             }
         }
@@ -220,10 +219,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
         named_bar_sync(1, CW * 32);
         if (warp == 0) {
             const double bp = warp_det_sum(qs, nrows, lane);
-            if (lane == 0) {
-                store_out(a, obase + a.maxrows + c, lbase + a.maxrows + c, tag, bp);
-                trace_stamp(rec, 6);
-            }
+            store_out(a, obase + a.maxrows + c, lbase + a.maxrows + c, tag, bp, lane);
+            if (lane == 0) trace_stamp(rec, 6);
         }
     }
 }
@@ -287,18 +284,16 @@ __global__ void __launch_bounds__(W * 32) gemv_ldg_kernel(const GemvArgs a)
         for (int s = 0; s < RPW; ++s) {
             if (s < nv) {
                 const double y = warp_butterfly(__dadd_rn(acc0[s], acc1[s]));
-                if (lane == 0) {
-                    const long long li = rg0 + s;
-                    store_out(a, obase + li, lbase + li, tag, y);
-                    qs[li - r0] = __dmul_rn(a.v[a.row0 + li], y);
-                }
+                const long long li = rg0 + s;
+                store_out(a, obase + li, lbase + li, tag, y, lane);
+                if (lane == 0) qs[li - r0] = __dmul_rn(a.v[a.row0 + li], y);
             }
         }
     }
     __syncthreads();
     if (warp == 0) {
         const double bp = warp_det_sum(qs, nrows, lane);
-        if (lane == 0) store_out(a, obase + a.maxrows + c, lbase + a.maxrows + c, tag, bp);
+        store_out(a, obase + a.maxrows + c, lbase + a.maxrows + c, tag, bp, lane);
     }
 }
 

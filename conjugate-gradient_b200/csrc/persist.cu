@@ -37,15 +37,28 @@ namespace cgb {
 
 namespace {
 
+// doubles of p a pipeline stage can hold = the widest tile a CTA may choose: an eighth of the
+// A slot (a 16-row x 512 slot may be used as 8 rows x 1024), never less than the nominal width
+__host__ __device__ constexpr int persist_pmax(int slot, int tc) { return slot / 8 > tc ? slot / 8 : tc; }
+// 256-chunks of the replicated vectors one CTA can own (their x, r, p live in registers: 9 warps
+// leave 168 registers per thread): N <= 2 * 148 * 256 = 75776; larger systems take the 3-kernel schedule
+constexpr int kPersistMaxChunks = 2;
+
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
 {
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_add_u32(unsigned *p, unsigned v)
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
 {
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v)
+{
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ double ld_cg_f64(const double *p)
 {
@@ -78,29 +91,71 @@ __device__ __noinline__ void spin_timeout(const PersistArgs &a, int what)
     __trap();
 }
 
-// Poll a counter another CTA of this GPU advances (one thread per CTA calls this).
-__device__ __forceinline__ void wait_counter(const PersistArgs &a, const unsigned *ctr, unsigned target, int what)
-{
-    if (ld_relaxed_u32(ctr) >= target) return;
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_relaxed_u32(ctr) < target) {
-        __nanosleep(32);
-        if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, what);
-    }
-}
-
 // One LL entry {lo, tag, hi, tag}: spin until both halves carry the tag.
 __device__ __forceinline__ double ll_wait(const PersistArgs &a, const uint4 *src, unsigned tag, uint4 v)
 {
     if (v.y != tag || v.w != tag) {
         const unsigned long long t0 = globaltimer_ns();
+        unsigned ns = 20;
         do {
-            __nanosleep(20);
+            __nanosleep(ns);
+            if (ns < 320) ns += ns; // early CTAs must not hammer L2 while the others still stream
             v = ld_volatile_v4(src);
             if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 1);
         } while (v.y != tag || v.w != tag);
     }
     return __hiloint2double((int)v.z, (int)v.x);
+}
+
+// PB LL entries at once: all pending loads are in flight together in every round (polling them
+// one after the other costs a round trip per late entry)
+template <int PB>
+__device__ __forceinline__ void ll_wait_batch(const PersistArgs &a, const uint4 *const (&src)[PB], unsigned pending,
+                                              unsigned tag, double (&out)[PB])
+{
+    uint4 v[PB];
+#pragma unroll
+    for (int u = 0; u < PB; ++u)
+        if ((pending >> u) & 1u) v[u] = ld_volatile_v4(src[u]);
+    unsigned long long t0 = 0;
+    unsigned ns = 20;
+    for (;;) {
+#pragma unroll
+        for (int u = 0; u < PB; ++u)
+            if (((pending >> u) & 1u) && v[u].y == tag && v[u].w == tag) {
+                out[u] = __hiloint2double((int)v[u].z, (int)v[u].x);
+                pending &= ~(1u << u);
+            }
+        if (!pending) return;
+        if (t0 == 0) t0 = globaltimer_ns();
+        __nanosleep(ns);
+        if (ns < 320) ns += ns; // early CTAs must not hammer L2 while the others still stream
+        if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 1);
+#pragma unroll
+        for (int u = 0; u < PB; ++u)
+            if ((pending >> u) & 1u) v[u] = ld_volatile_v4(src[u]);
+    }
+}
+
+// det_sum over shared memory with the loads of 8 terms in flight (the adds keep their order)
+__device__ __forceinline__ double warp_det_sum_smem(const double *v, int n, int lane)
+{
+    double s = 0.0;
+    int t = lane;
+    for (; t + 7 * 32 < n; t += 8 * 32) {
+        double x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = v[t + 32 * k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s = __dadd_rn(s, x[k]);
+    }
+    for (; t < n; t += 32) s = __dadd_rn(s, v[t]);
+    return warp_butterfly(s);
+}
+
+__device__ __forceinline__ void prefetch_l2_line(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // mbarrier wait with the configurable bound (a peer rank may legitimately be seconds late)
@@ -118,18 +173,20 @@ __device__ __forceinline__ void mbar_wait_ns(const PersistArgs &a, uint64_t *bar
 template <int CW, int RPW, int TC, int STAGES, int MAXC>
 __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const PersistArgs a)
 {
-    constexpr int TR = CW * RPW;
-    constexpr int NCT = CW * 32;       // consumer threads
-    constexpr int EPT = kChunk / NCT;  // elements of a 256-chunk per consumer thread
+    constexpr int TR = CW * RPW;            // most rows of a row block
+    constexpr int SLOT = TR * TC;           // doubles of A per pipeline stage
+    constexpr int PMAX = persist_pmax(SLOT, TC);  // doubles of p per pipeline stage = widest tile
+    constexpr int NCT = CW * 32;            // consumer threads
+    constexpr int EPT = kChunk / NCT;       // elements of a 256-chunk per consumer thread
     static_assert(CW == 4 || CW == 8, "chunk256 mapping is written for 4 or 8 consumer warps");
     static_assert(TC % 64 == 0, "tile width must be a multiple of 64 doubles");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sA = reinterpret_cast<double *>(smem_raw);            // [STAGES][TR][TC]
-    double *sP = sA + (size_t)STAGES * TR * TC;                   // [STAGES][TC]
-    uint64_t *full = reinterpret_cast<uint64_t *>(sP + (size_t)STAGES * TC);
+    double *sA = reinterpret_cast<double *>(smem_raw);            // [STAGES][SLOT]
+    double *sP = sA + (size_t)STAGES * SLOT;                      // [STAGES][PMAX]
+    uint64_t *full = reinterpret_cast<uint64_t *>(sP + (size_t)STAGES * PMAX);
     uint64_t *empty = full + STAGES;
-    double *wsum = reinterpret_cast<double *>(empty + STAGES);    // [8]
-    double *s_sc = wsum + 8;                                      // [4] broadcast scalars
+    double *wsum = reinterpret_cast<double *>(empty + STAGES);    // [MAXC][8]
+    double *s_sc = wsum + MAXC * 8;                               // [4] broadcast scalars
     double *qs = s_sc + 4;                                        // [rows of this CTA]
     double *scr = qs + a.qs_n;                                    // [max(world * grid, nchunks)]
     __shared__ volatile int s_stop;                               // consumers -> producer: loop left
@@ -140,8 +197,23 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
     const long long r1 = (long long)(c + 1) * a.rows / nblk;
     const int nrows = (int)(r1 - r0);
     const int nb = (nrows + TR - 1) / TR;          // row blocks, balanced below
-    const int ntc = (int)((a.ld + TC - 1) / TC);   // column tiles
-    const unsigned T = (unsigned)nb * (unsigned)ntc; // pipeline steps per mat-vec
+    // Tile width of a row block: as wide as the stage allows for its rows, so that a stage is
+    // (nearly) full whatever the rows-per-CTA ratio -- under a saturated memory system an SM's
+    // share of the HBM stream is proportional to its bytes in flight (34 rows per CTA = blocks of
+    // 11, 11, 12 rows would fill 16-row x 512 tiles to 70 % only).  Any multiple of 64 keeps the
+    // summation order.  The balanced split gives blocks of `lo` or `lo + 1` rows.
+    const int lo = nb ? nrows / nb : 1;
+    auto width_of = [&](int nr) {
+        int w = (SLOT / nr) & ~63;
+        return w > PMAX ? PMAX : w;
+    };
+    const int w_lo = width_of(lo), w_hi = width_of(lo + 1);
+    const int ntc_lo = (int)((a.ld + w_lo - 1) / w_lo), ntc_hi = (int)((a.ld + w_hi - 1) / w_hi);
+    const int n_hi = nb ? nrows - lo * nb : 0;     // blocks with lo + 1 rows
+    const unsigned T = (unsigned)(nb - n_hi) * (unsigned)ntc_lo + (unsigned)n_hi * (unsigned)ntc_hi; // steps per mat-vec
+    __shared__ long long s_c0[8]; // per stage: first column and width of the tile in flight (producer only)
+    __shared__ int s_w[8];
+    static_assert(STAGES <= 8, "stage metadata");
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -161,36 +233,47 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
         if (T == 0) return;
         const uint64_t pol_a = l2_policy_evict_first();
         const uint64_t pol_p = l2_policy_evict_last();
-        // global step g -> (row block b, column tile t) of mat-vec g / T
-        auto geom = [&](unsigned g, long long &rb0, int &nr, long long &c0, int &w) {
-            const unsigned l = g % T;
-            const int b = (int)(l / (unsigned)ntc), t = (int)(l - (unsigned)b * (unsigned)ntc);
-            rb0 = r0 + (long long)b * nrows / nb;
-            nr = (int)(r0 + (long long)(b + 1) * nrows / nb - rb0);
-            c0 = (long long)t * TC;
-            w = (int)((a.ld - c0 < TC) ? (a.ld - c0) : TC);
+        // cursor over the pipeline steps (row block b, column tile t), wrapping from one mat-vec
+        // into the next
+        struct Cur {
+            int b, t, nr, wdb, ntb;
+            long long rb0;
         };
-        auto issueA = [&](unsigned g) {
-            long long rb0, c0;
-            int nr, w;
-            geom(g, rb0, nr, c0, w);
+        auto cur_block = [&](Cur &k, int b) {
+            k.b = b;
+            k.t = 0;
+            k.rb0 = r0 + (long long)b * nrows / nb;
+            k.nr = (int)(r0 + (long long)(b + 1) * nrows / nb - k.rb0);
+            k.wdb = (k.nr == lo) ? w_lo : w_hi;
+            k.ntb = (k.nr == lo) ? ntc_lo : ntc_hi;
+        };
+        auto cur_next = [&](Cur &k) {
+            if (++k.t == k.ntb) cur_block(k, (k.b + 1 == nb) ? 0 : k.b + 1);
+        };
+        auto issueA = [&](unsigned g, const Cur &k) {
+            const long long c0 = (long long)k.t * k.wdb;
+            const int w = (int)((a.ld - c0 < k.wdb) ? (a.ld - c0) : k.wdb);
             const int stage = g % STAGES;
-            if (lane == 0) mbar_arrive_expect_tx(&full[stage], (unsigned)((nr + 1) * w * 8));
+            if (lane == 0) {
+                s_c0[stage] = c0;
+                s_w[stage] = w;
+                mbar_arrive_expect_tx(&full[stage], (unsigned)((k.nr + 1) * w * 8));
+            }
             __syncwarp();
-            double *dstA = sA + (size_t)stage * TR * TC;
-            for (int j = lane; j < nr; j += 32)
-                bulk_g2s(dstA + (size_t)j * TC, a.A + (rb0 + j) * a.ld + c0, (unsigned)(w * 8), &full[stage], pol_a);
+            double *dstA = sA + (size_t)stage * SLOT;
+            for (int j = lane; j < k.nr; j += 32)
+                bulk_g2s(dstA + (size_t)j * k.wdb, a.A + (k.rb0 + j) * a.ld + c0, (unsigned)(w * 8), &full[stage], pol_a);
         };
         auto issueP = [&](unsigned g) {
-            long long rb0, c0;
-            int nr, w;
-            geom(g, rb0, nr, c0, w);
             const int stage = g % STAGES;
-            if (lane == 0) bulk_g2s(sP + (size_t)stage * TC, a.p + c0, (unsigned)(w * 8), &full[stage], pol_p);
+            if (lane == 0)
+                bulk_g2s(sP + (size_t)stage * PMAX, a.p + s_c0[stage], (unsigned)(s_w[stage] * 8), &full[stage], pol_p);
         };
         auto wait_empty = [&](unsigned g) {
             if (g >= (unsigned)STAGES) mbar_wait_ns(a, &empty[g % STAGES], ((g / STAGES) & 1u) ^ 1u);
         };
+        Cur cur;
+        cur_block(cur, 0);
         unsigned pre = 0; // steps of the coming mat-vec whose A part is already in flight
         for (int m = 0; m < a.iters; ++m) {
             const unsigned base = (unsigned)m * T;
@@ -201,14 +284,14 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                 if (lane == 0) {
                     const unsigned target = nchunks * (unsigned)m;
                     const unsigned long long t0 = globaltimer_ns();
-                    while (ld_relaxed_u32(&a.sync->arrive_p) < target) {
+                    while (ld_acquire_u32(&a.sync->arrive_p) < target) {
                         if (s_stop) {
                             stop = 1;
                             break;
                         }
-                        __nanosleep(32);
                         if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 4);
                     }
+                    fence_proxy_async_global(); // the chunk owners' stores to p are read through the async proxy (TMA)
                 }
                 stop = __shfl_sync(0xffffffffu, stop, 0);
                 if (stop) {
@@ -216,32 +299,37 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                     for (unsigned u = 0; u < pre; ++u) mbar_wait_ns(a, &full[(base + u) % STAGES], ((base + u) / STAGES) & 1u);
                     return;
                 }
-                __threadfence();            // acquire: the chunk owners' stores to p ...
-                fence_proxy_async_global(); // ... are read below through the async proxy (TMA)
             }
             for (unsigned u = 0; u < pre; ++u) issueP(base + u);
             for (unsigned g = base + pre; g < base + T; ++g) {
                 wait_empty(g);
-                issueA(g);
+                issueA(g, cur);
+                cur_next(cur);
                 issueP(g);
             }
             pre = 0;
             if (m + 1 < a.iters) {
-                // run ahead into the next mat-vec: A tiles into the ring as its stages drain, the
-                // steps after them into L2, while the vector phases of this iteration run
+                // run ahead into the next mat-vec: A tiles into the ring as its stages drain (A
+                // never changes), while the vector phases of this iteration run
                 const unsigned npre = T < (unsigned)STAGES ? T : (unsigned)STAGES;
                 for (; pre < npre; ++pre) {
                     wait_empty(base + T + pre);
-                    issueA(base + T + pre);
+                    issueA(base + T + pre, cur);
+                    cur_next(cur);
                 }
-                unsigned npf = pre + (unsigned)a.l2_prefetch;
-                if (npf > T) npf = T;
-                for (unsigned u = pre; u < npf; ++u) {
-                    long long rb0, c0;
-                    int nr, w;
-                    geom(base + T + u, rb0, nr, c0, w);
-                    for (int j = lane; j < nr; j += 32)
-                        bulk_prefetch_l2(a.A + (rb0 + j) * a.ld + c0, (unsigned)(w * 8));
+                Cur pf = cur; // ... and the steps after them into L2
+                for (int u = 0; u < a.l2_prefetch && (unsigned)u + pre < T; ++u) {
+                    const long long c0 = (long long)pf.t * pf.wdb;
+                    const int w = (int)((a.ld - c0 < pf.wdb) ? (a.ld - c0) : pf.wdb);
+                    if (a.l2_prefetch_mode == 0) {
+                        for (int j = lane; j < pf.nr; j += 32)
+                            bulk_prefetch_l2(a.A + (pf.rb0 + j) * a.ld + c0, (unsigned)(w * 8));
+                    } else { // one 128-byte line per lane and instruction
+                        for (int j = 0; j < pf.nr; ++j)
+                            for (int q = lane * 16; q < w; q += 32 * 16)
+                                prefetch_l2_line(a.A + (pf.rb0 + j) * a.ld + c0 + q);
+                    }
+                    cur_next(pf);
                 }
             }
         }
@@ -287,13 +375,13 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
     double rsnew = rsold, alpha = 0.0, conj = 0.0;
     int converged = 0, executed = 0;
 
-    const uint4 *const own_ll = a.ll;
     unsigned g = 0; // pipeline step counter, never reset (mbarrier parities)
     for (int m = 0; m < a.iters; ++m) {
         const long long jloop = it0 + 1 + m;             // the reference's k of this loop body
         const unsigned tag = epoch0 + 1u + (unsigned)m;  // tag + buffer of this exchange
         const long long lbase = (long long)(tag & 1u) * a.bufstride + a.slot_off;
-        const uint4 *const view = own_ll + (long long)(tag & 1u) * a.bufstride;
+        const uint4 *const view = a.ll + (long long)(tag & 1u) * a.bufstride;
+        uint4 *const rrview = a.rr_ll + (long long)(tag & 1u) * a.rr_stride;
         unsigned long long *rec = nullptr;
         if (trace && tid == 0) {
             rec = trace + ((size_t)((tr0 + (unsigned)m) % (unsigned)a.trace.cap) * (size_t)nblk + (size_t)c) * kTraceWords;
@@ -306,6 +394,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
             const long long rb0 = r0 + (long long)b * nrows / nb;
             const int nr = (int)(r0 + (long long)(b + 1) * nrows / nb - rb0);
             const int nv = (nr > warp) ? ((nr - warp + CW - 1) / CW) : 0;
+            const int wd = (nr == lo) ? w_lo : w_hi;
+            const int ntc = (nr == lo) ? ntc_lo : ntc_hi;
             double acc0[RPW], acc1[RPW], prow[RPW];
 #pragma unroll
             for (int s = 0; s < RPW; ++s) {
@@ -316,8 +406,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
             for (int t = 0; t < ntc; ++t, ++g) {
                 const int stage = g % STAGES;
                 const unsigned ph = (g / STAGES) & 1u;
-                const long long c0 = (long long)t * TC;
-                const int w = (int)((a.ld - c0 < TC) ? (a.ld - c0) : TC);
+                const long long c0 = (long long)t * wd;
+                const int w = (int)((a.ld - c0 < wd) ? (a.ld - c0) : wd);
                 mbar_wait_ns(a, &full[stage], ph);
                 if (t == 0) {
                     // the tile carries a p slice, so every chunk of p has been published:
@@ -327,16 +417,28 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                     for (int s = 0; s < RPW; ++s)
                         if (s < nv) prow[s] = ld_cg_f64(a.p + a.row0 + rb0 + warp + s * CW);
                 }
-                const double2 *sa2 = reinterpret_cast<const double2 *>(sA + (size_t)stage * TR * TC);
-                const double2 *sp2 = reinterpret_cast<const double2 *>(sP + (size_t)stage * TC);
-                if (nv == RPW && w == TC) {
-#pragma unroll
-                    for (int i = 0; i < TC / 64; ++i) {
+                const double2 *sa2 = reinterpret_cast<const double2 *>(sA + (size_t)stage * SLOT);
+                const double2 *sp2 = reinterpret_cast<const double2 *>(sP + (size_t)stage * PMAX);
+                const int pitch2 = wd >> 1; // tile row pitch in 16-byte chunks
+                if (nv == RPW) {
+                    const int full_it = w >> 6; // 64 columns per warp pass
+#pragma unroll 4
+                    for (int i = 0; i < full_it; ++i) {
                         const int q = lane + 32 * i;
                         const double2 pv = sp2[q];
 #pragma unroll
                         for (int s = 0; s < RPW; ++s) {
-                            const double2 av = sa2[(warp + s * CW) * (TC / 2) + q];
+                            const double2 av = sa2[(warp + s * CW) * pitch2 + q];
+                            acc0[s] = __fma_rn(av.x, pv.x, acc0[s]);
+                            acc1[s] = __fma_rn(av.y, pv.y, acc1[s]);
+                        }
+                    }
+                    const int q = lane + 32 * full_it; // ragged end of the last tile (ld is a multiple of 16)
+                    if (q < (w >> 1)) {
+                        const double2 pv = sp2[q];
+#pragma unroll
+                        for (int s = 0; s < RPW; ++s) {
+                            const double2 av = sa2[(warp + s * CW) * pitch2 + q];
                             acc0[s] = __fma_rn(av.x, pv.x, acc0[s]);
                             acc1[s] = __fma_rn(av.y, pv.y, acc1[s]);
                         }
@@ -348,7 +450,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
 #pragma unroll
                         for (int s = 0; s < RPW; ++s) {
                             if (s < nv) {
-                                const double2 av = sa2[(warp + s * CW) * (TC / 2) + q];
+                                const double2 av = sa2[(warp + s * CW) * pitch2 + q];
                                 acc0[s] = __fma_rn(av.x, pv.x, acc0[s]);
                                 acc1[s] = __fma_rn(av.y, pv.y, acc1[s]);
                             }
@@ -362,54 +464,46 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
 #pragma unroll
             for (int s = 0; s < RPW; ++s) {
                 if (s < nv) {
-                    const double y = warp_butterfly(__dadd_rn(acc0[s], acc1[s]));
-                    if (lane == 0) {
-                        const long long li = rb0 + warp + s * CW;
-#pragma unroll
-                        for (int gg = 0; gg < kMaxWorld; ++gg)
-                            if (gg < a.world) ll_store(a.peer_ll[gg] + lbase + li, y, tag);
-                        qs[li - r0] = __dmul_rn(prow[s], y);
-                    }
+                    const double y = warp_butterfly(__dadd_rn(acc0[s], acc1[s])); // every lane holds y
+                    const long long li = rb0 + warp + s * CW;
+                    // lane g stores to rank g: ONE store instruction, `world` transactions in flight
+                    // (a loop in one lane would serialise the strong.sys stores, ~0.35 us each)
+                    if (lane < a.world) ll_store(a.peer_ll[lane] + lbase + li, y, tag);
+                    if (lane == 0) qs[li - r0] = __dmul_rn(prow[s], y);
                 }
             }
         }
         named_bar_sync(1, NCT);
         if (warp == 0) {
             const double bp = warp_det_sum(qs, nrows, lane); // level 1 of p'Ap (cg.cc:105)
-            if (lane == 0) {
-#pragma unroll
-                for (int gg = 0; gg < kMaxWorld; ++gg)
-                    if (gg < a.world) ll_store(a.peer_ll[gg] + lbase + a.maxrows + c, bp, tag);
-                red_add_u32(&a.sync->arrive_mv, 1u); // a hint for the local waiters, not a flag
-                if (rec) rec[5] = globaltimer_ns();
-                // cheap gate before anybody polls LL entries: all CTAs of THIS GPU are through
-                wait_counter(a, &a.sync->arrive_mv, (unsigned)nblk * (unsigned)(m + 1), 2);
-            }
+            if (lane < a.world) ll_store(a.peer_ll[lane] + lbase + a.maxrows + c, bp, tag);
+            if (lane == 0 && rec) rec[5] = globaltimer_ns();
         }
-        named_bar_sync(1, NCT);
 
         // ------------------------------------------------ phase U: alpha, x, r, r'r partials (cg.cc:105-116)
         {
+            // every block partial of every rank: polled straight from the LL entries, 5 in flight
             const int total = a.world * nblk;
-            for (int t0 = tid; t0 < total; t0 += 4 * NCT) {
-                uint4 v[4];
-                const uint4 *src[4];
+            constexpr int PB = 5;
+            for (int t0 = tid; t0 < total; t0 += PB * NCT) {
+                const uint4 *src[PB];
+                double val[PB];
+                unsigned pending = 0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < PB; ++u) {
                     const int t = t0 + u * NCT;
                     const int rk = t / nblk, cb = t - rk * nblk;
                     src[u] = view + (long long)rk * a.slot + a.maxrows + cb;
-                    if (t < total) v[u] = ld_volatile_v4(src[u]);
+                    if (t < total) pending |= 1u << u;
                 }
+                ll_wait_batch<PB>(a, src, pending, tag, val);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int t = t0 + u * NCT;
-                    if (t < total) scr[t] = ll_wait(a, src[u], tag, v[u]);
-                }
+                for (int u = 0; u < PB; ++u)
+                    if (t0 + u * NCT < total) scr[t0 + u * NCT] = val[u];
             }
             named_bar_sync(1, NCT);
             if (warp == 0) {
-                const double cj = warp_det_sum(scr, total, lane);                 // p'Ap, every rank's blocks
+                const double cj = warp_det_sum_smem(scr, total, lane);            // p'Ap, every rank's blocks
                 const double clamp = __dmul_rn(rsold, kNearZero);
                 const double al = __ddiv_rn(rsold, (cj < clamp) ? clamp : cj);    // cg.cc:107
                 if (lane == 0) {
@@ -417,65 +511,91 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                     s_sc[3] = cj;
                 }
             }
-            named_bar_sync(1, NCT);
-            alpha = s_sc[1];
-            conj = s_sc[3];
-            if (rec) rec[1] = globaltimer_ns();
         }
+        // the Ap values of the own chunks (all block partials are in, so these rows are too --
+        // up to reordering of a peer's stores, which the entries' own flags cover)
+        double apv[MAXC * EPT];
+        {
+            const uint4 *esrc[MAXC * EPT];
+            unsigned pending = 0;
+#pragma unroll
+            for (int cc = 0; cc < MAXC; ++cc) {
+                const long long j = (long long)c + (long long)cc * nblk;
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const long long i = j * kChunk + tid + e * NCT;
+                    const bool ok = j < a.nchunks && i < a.n;
+                    esrc[cc * EPT + e] = view + gather_index_raw(a.n_loc, a.world, a.slot, ok ? i : 0);
+                    if (ok) pending |= 1u << (cc * EPT + e);
+                }
+            }
+            ll_wait_batch<MAXC * EPT>(a, esrc, pending, tag, apv);
+        }
+        named_bar_sync(1, NCT);
+        alpha = s_sc[1];
+        conj = s_sc[3];
+        if (rec) rec[1] = globaltimer_ns();
 #pragma unroll
         for (int cc = 0; cc < MAXC; ++cc) {
             const long long j = (long long)c + (long long)cc * nblk;
-            if (j < a.nchunks) { // uniform over the CTA
-                double v = 0.0;
-                uint4 e4[EPT];
-                const uint4 *esrc[EPT];
+            double v = 0.0;
 #pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    const long long i = j * kChunk + tid + e * NCT;
-                    esrc[e] = view + gather_index_raw(a.n_loc, a.world, a.slot, i < a.n ? i : 0);
-                    if (i < a.n) e4[e] = ld_volatile_v4(esrc[e]);
+            for (int e = 0; e < EPT; ++e) {
+                const long long i = j * kChunk + tid + e * NCT;
+                double sq = 0.0;
+                if (j < a.nchunks && i < a.n) {
+                    const double ap = apv[cc * EPT + e];
+                    xs[cc][e] = __fma_rn(alpha, ps[cc][e], xs[cc][e]);   // cg.cc:110
+                    rs[cc][e] = __fma_rn(-alpha, ap, rs[cc][e]);        // cg.cc:113
+                    sq = __dmul_rn(rs[cc][e], rs[cc][e]);               // cg.cc:116
                 }
+                const double bf = warp_butterfly(sq);                   // 32-group warp + e * CW
+                v = (e == 0) ? bf : __dadd_rn(v, bf);                   // group g + group g + 4
+            }
+            if (lane == 0) wsum[cc * 8 + warp] = v;
+        }
+        named_bar_sync(1, NCT);
+        if (warp == 0) {
+            // chunk256: the remaining levels of the perfect tree, across the consumer warps;
+            // the partial is PUBLISHED as a self-flagging LL entry (no fence, no counter)
 #pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    const long long i = j * kChunk + tid + e * NCT;
-                    double sq = 0.0;
-                    if (i < a.n) {
-                        const double ap = ll_wait(a, esrc[e], tag, e4[e]);
-                        xs[cc][e] = __fma_rn(alpha, ps[cc][e], xs[cc][e]);   // cg.cc:110
-                        rs[cc][e] = __fma_rn(-alpha, ap, rs[cc][e]);        // cg.cc:113
-                        sq = __dmul_rn(rs[cc][e], rs[cc][e]);               // cg.cc:116
-                    }
-                    const double bf = warp_butterfly(sq);                   // 32-group warp + e * CW
-                    v = (e == 0) ? bf : __dadd_rn(v, bf);                   // group g + group g + 4
-                }
-                // chunk256: the remaining levels of the perfect tree, across the consumer warps
-                if (lane == 0) wsum[warp] = v;
-                named_bar_sync(1, NCT);
-                if (warp == 0) {
-                    double t = (lane < CW) ? wsum[lane] : 0.0;
+            for (int cc = 0; cc < MAXC; ++cc) {
+                const long long j = (long long)c + (long long)cc * nblk;
+                if (j < a.nchunks) {
+                    double t = (lane < CW) ? wsum[cc * 8 + lane] : 0.0;
                     if (CW == 8) t = __dadd_rn(t, shfl_xor_f64(t, 4));
                     t = __dadd_rn(t, shfl_xor_f64(t, 2));
                     t = __dadd_rn(t, shfl_xor_f64(t, 1));
-                    if (lane == 0) a.rrpart[j] = t;
+                    if (lane == 0) {
+                        ll_store(rrview + j, t, tag);
+                        a.rrpart[j] = t; // hand-over to the next launch / cgb_solve_end
+                    }
                 }
-                named_bar_sync(1, NCT);
-            }
-        }
-        if (tid == 0) {
-            if (mychunks) {
-                __threadfence(); // release rrpart[own chunks]
-                red_add_u32(&a.sync->arrive_rr, mychunks);
             }
             if (rec) rec[2] = globaltimer_ns();
-            // ------------------------------------------------ phase B: r'r, stop test, beta (cg.cc:116-124)
-            wait_counter(a, &a.sync->arrive_rr, nchunks * (unsigned)(m + 1), 3);
-            __threadfence(); // acquire
+        }
+
+        // ------------------------------------------------ phase B: r'r, stop test, beta (cg.cc:116-124)
+        {
+            constexpr int PB = 3;
+            for (unsigned t0 = tid; t0 < nchunks; t0 += PB * NCT) {
+                const uint4 *src[PB];
+                double val[PB];
+                unsigned pending = 0;
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    src[u] = rrview + t0 + u * NCT;
+                    if (t0 + u * NCT < nchunks) pending |= 1u << u;
+                }
+                ll_wait_batch<PB>(a, src, pending, tag, val);
+#pragma unroll
+                for (int u = 0; u < PB; ++u)
+                    if (t0 + u * NCT < nchunks) scr[t0 + u * NCT] = val[u];
+            }
         }
         named_bar_sync(1, NCT);
-        for (unsigned t = tid; t < nchunks; t += NCT) scr[t] = ld_cg_f64(a.rrpart + t);
-        named_bar_sync(1, NCT);
         if (warp == 0) {
-            const double s = warp_det_sum(scr, nchunks, lane);
+            const double s = warp_det_sum_smem(scr, (int)nchunks, lane);
             if (lane == 0) s_sc[2] = s;
         }
         named_bar_sync(1, NCT);
@@ -502,13 +622,14 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                 }
             }
         }
-        named_bar_sync(1, NCT);
-        if (tid == 0) {
-            if (mychunks) {
-                __threadfence(); // release p[own chunks] to every CTA's producer
-                red_add_u32(&a.sync->arrive_p, mychunks);
+        if (mychunks) {
+            named_bar_sync(1, NCT);
+            if (tid == 0) {
+                red_release_add_u32(&a.sync->arrive_p, mychunks); // release p[own chunks] to every CTA's producer
+                if (rec) rec[6] = globaltimer_ns();
             }
-            if (rec) rec[6] = globaltimer_ns();
+        } else if (rec) {
+            rec[6] = globaltimer_ns();
         }
     }
 
@@ -531,18 +652,15 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
         st->conj = conj;
         st->alpha = alpha;
         st->rsnew = rsnew;
+        st->rsold = rsold; // converged: the STALE rsold the reference prints (cg.cc:152-153)
+        // not converged: "inside loop body it0 + executed" -- rrpart holds its r'r partials; the next
+        // launch (or cgb_solve_end) does the deferred rsold = rsnew / iter + 1, as in vec.cu.
+        // converged: k = loop index at the break.  Both are it0 + executed.
+        st->iter = it0 + executed;
         if (converged) {
-            // the reference prints the STALE rsold and k = loop index at the break
-            st->rsold = rsold;
-            st->iter = it0 + executed;
             st->done = 1;
             if (a.host_done) *a.host_done = 1;
             __threadfence_system();
-        } else {
-            // "inside loop body it0 + executed": rrpart holds its r'r partials; the next launch
-            // (or cgb_solve_end) does the deferred rsold = rsnew / iter + 1, as in vec.cu
-            st->rsold = rsold;
-            st->iter = it0 + executed;
         }
         a.ctl->epoch = a.ctl->epoch + (unsigned long long)executed;
     }
@@ -554,11 +672,9 @@ namespace {
 template <int CW, int RPW, int TC, int STAGES>
 size_t persist_smem(const PersistArgs &a)
 {
-    return (size_t)STAGES * CW * RPW * TC * 8 + (size_t)STAGES * TC * 8 + 2 * STAGES * 8 + (8 + 4) * 8 +
-           ((size_t)a.qs_n + (size_t)a.scr_n) * 8;
+    return (size_t)STAGES * CW * RPW * TC * 8 + (size_t)STAGES * persist_pmax(CW * RPW * TC, TC) * 8 + 2 * STAGES * 8 +
+           (kPersistMaxChunks * 8 + 4) * 8 + ((size_t)a.qs_n + (size_t)a.scr_n) * 8;
 }
-
-constexpr int kPersistMaxChunks = 4; // 256-chunks of the vectors per CTA (N <= 4 * 148 * 256)
 
 template <int CW, int RPW, int TC, int STAGES>
 cudaError_t persist_launch(const PersistArgs &a, int nblk, cudaStream_t s)
@@ -598,9 +714,7 @@ cudaError_t persist_preload()
 const PersistVariant kPersist[] = {
     // the tile shapes of the gemv.cu variants of the same name (1 CTA per SM, 4 or 8 consumer warps)
     {"tma_w8r2c512s3", persist_launch<8, 2, 512, 3>, persist_preload<8, 2, 512, 3>, persist_smem_fixed<8, 2, 512, 3>},
-    {"tma_w8r1c512s6", persist_launch<8, 1, 512, 6>, persist_preload<8, 1, 512, 6>, persist_smem_fixed<8, 1, 512, 6>},
     {"tma_w4r4c512s3", persist_launch<4, 4, 512, 3>, persist_preload<4, 4, 512, 3>, persist_smem_fixed<4, 4, 512, 3>},
-    {"tma_w8r2c256s6", persist_launch<8, 2, 256, 6>, persist_preload<8, 2, 256, 6>, persist_smem_fixed<8, 2, 256, 6>},
     {"tma_w8r1c1024s3", persist_launch<8, 1, 1024, 3>, persist_preload<8, 1, 1024, 3>, persist_smem_fixed<8, 1, 1024, 3>},
     {"tma_w4r2c1024s3", persist_launch<4, 2, 1024, 3>, persist_preload<4, 2, 1024, 3>, persist_smem_fixed<4, 2, 1024, 3>},
     {"tma_w4r1c2048s2", persist_launch<4, 1, 2048, 2>, persist_preload<4, 1, 2048, 2>, persist_smem_fixed<4, 1, 2048, 2>},

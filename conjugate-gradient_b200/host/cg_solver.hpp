@@ -71,6 +71,7 @@ private:
     void ensure_contexts(int64_t n);
     void destroy_contexts();
     void run_solve(double *x, int64_t max_iter);
+    void autotune();
     template <class F> void on_all_ranks(F &&f);
 
     int m_m{0};

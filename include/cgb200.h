@@ -138,6 +138,16 @@ int cgb_get_option(cgb_ctx *ctx, const char *key, int64_t *value);
 int cgb_gemv_variant_count(void);
 const char *cgb_gemv_variant_name(int variant);
 
+/* One-off choice of the mat-vec tile shape ("gemv_variant") for this rank's shard shape on this
+ * GPU: every candidate shape runs `iters` (<= 0: 12) loop bodies of the schedule in use on the
+ * resident matrix, the fastest becomes the configured variant.  Call it after the matrix is
+ * set and OUTSIDE any timed region (the reference's timer brackets solve() only,
+ * code/MPI/cg_main.cc:53-55).  A rank of world > 1 tunes alone (its exchange looped back to
+ * itself); peers must not be inside a solve meanwhile.  All shapes share one summation order:
+ * the choice never changes a result bit.  us_per_iter (nullable, cgb_gemv_variant_count()
+ * floats) receives the time of every candidate, < 0 for shapes that were not candidates. */
+int cgb_autotune(cgb_ctx *ctx, int iters, int *chosen, float *us_per_iter);
+
 typedef struct cgb_layout {
     int64_t n, ld, rows, row0; /* shard geometry */
     int rank, world, device;

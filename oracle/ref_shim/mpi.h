@@ -1,7 +1,8 @@
 /*
  * mpi.h -- single-process stand-in for the seven MPI entry points the
  * reference MPI solver uses (/root/reference/code/MPI/cg.cc:50-142,
- * cg_main.cc:15-20,67).  There is no MPI in this image; this header lets the
+ * cg_main.cc:15-20,67), plus the three the libcgb200 binding of INTEGRATION.md B adds
+ * (MPI_Allgather of the exchange blobs, MPI_Barrier, MPI_Abort; ref_shim/cg_cgb.cc).  There is no MPI in this image; this header lets the
  * reference sources compile UNMODIFIED.  Test infrastructure only (oracle/).
  *
  * Rank count: 1.  The definitions live in mpi_single.cc so that a multi-rank
@@ -16,6 +17,7 @@ typedef int MPI_Op;
 
 #define MPI_COMM_WORLD 0
 #define MPI_DOUBLE 8
+#define MPI_BYTE 1
 #define MPI_SUM 1
 #define MPI_THREAD_SINGLE 0
 #define MPI_SUCCESS 0
@@ -36,6 +38,11 @@ int MPI_Allgatherv(const void *sendbuf, int sendcount, MPI_Datatype sendtype, vo
 int MPI_Gatherv(const void *sendbuf, int sendcount, MPI_Datatype sendtype, void *recvbuf,
                 const int *recvcounts, const int *displs, MPI_Datatype recvtype, int root,
                 MPI_Comm comm);
+
+int MPI_Allgather(const void *sendbuf, int sendcount, MPI_Datatype sendtype, void *recvbuf,
+                  int recvcount, MPI_Datatype recvtype, MPI_Comm comm);
+int MPI_Barrier(MPI_Comm comm);
+int MPI_Abort(MPI_Comm comm, int errorcode);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <csignal>
 #include <pthread.h>
 #include <sys/mman.h>
 #include <sys/wait.h>
@@ -182,6 +183,38 @@ int MPI_Gatherv(const void *sendbuf, int sendcount, MPI_Datatype sendtype, void 
         }
     }
     return MPI_SUCCESS;
+}
+
+// the libcgb200 binding (ref_shim/cg_cgb.cc): exchange blobs, a barrier before teardown, abort
+int MPI_Allgather(const void *sendbuf, int sendcount, MPI_Datatype sendtype, void *recvbuf, int,
+                  MPI_Datatype, MPI_Comm)
+{
+    const size_t bytes = (size_t)sendcount * (size_t)sendtype;
+    if (g_size == 1) {
+        std::memcpy(recvbuf, sendbuf, bytes);
+        return MPI_SUCCESS;
+    }
+    if (bytes * (size_t)g_size > sizeof(g_sh->exchange)) die("exchange buffer too small");
+    char *ex = reinterpret_cast<char *>(g_sh->exchange);
+    std::memcpy(ex + bytes * (size_t)g_rank, sendbuf, bytes);
+    barrier();
+    std::memcpy(recvbuf, ex, bytes * (size_t)g_size);
+    barrier();
+    return MPI_SUCCESS;
+}
+
+int MPI_Barrier(MPI_Comm)
+{
+    barrier();
+    return MPI_SUCCESS;
+}
+
+int MPI_Abort(MPI_Comm, int errorcode)
+{
+    std::fflush(nullptr);
+    if (g_rank == 0)
+        for (pid_t pid : g_children) kill(pid, SIGTERM);
+    std::_Exit(errorcode ? errorcode : 1);
 }
 
 } // extern "C"

@@ -95,6 +95,42 @@ def summarize(g, xr, p, rows, n, skip=4):
     return out
 
 
+def summarize_persistent(g, rows, n, skip=4):
+    """g: [L, nblk, 8] records of the persistent kernel (one per iteration and CTA): 0 iteration
+    start, 3 first tile consumed, 5 rows + block partial stored, 1 alpha known, 2 own r'r partials
+    published, 4 beta known, 6 own p chunks published."""
+    g = g.astype(np.int64)
+    L = g.shape[0]
+    t0, alpha, rrpub, first, beta, rowsd, ppub = (g[:, :, i] for i in range(7))
+    sl = slice(skip, L - 1)
+    it = np.diff(rowsd.max(axis=1))[skip:]
+    med = lambda a: us(np.median(a))
+    last_rows = rowsd.max(axis=1)
+    out = {
+        "launches": int(L), "ctas": int(g.shape[1]),
+        "iter_us": med(it), "iter_us_min": us(it.min()), "iter_us_max": us(it.max()),
+        "stream_gbs_iter": 8.0 * rows * n / (np.median(it) * 1e-9) / 1e9,
+        # per-CTA phase durations (medians over CTAs and iterations)
+        "M_first_tile_to_rows_done_us": med((rowsd - first)[sl]),
+        "start_to_first_tile_us": med((first - t0)[sl]),
+        "rows_done_spread_max_min_us": med((rowsd.max(axis=1) - rowsd.min(axis=1))[sl]),
+        "rows_done_spread_max_med_us": med((rowsd.max(axis=1) - np.median(rowsd, axis=1))[sl]),
+        # the chain after the LAST CTA of the GPU has stored its rows
+        "chain_us": {
+            "last_rows_done->alpha(med cta)": med((np.median(alpha, axis=1) - last_rows)[sl]),
+            "alpha->rr_published(med)": med((rrpub - alpha)[sl]),
+            "alpha->rr_published(max cta)": med((rrpub - alpha).max(axis=1)[sl]),
+            "last_rr_published->beta(med cta)": med((np.median(beta, axis=1) - rrpub.max(axis=1))[sl]),
+            "beta->p_published(med)": med((ppub - beta)[sl]),
+            "last_p_published->first_tile_next(med cta)": med((np.median(first[1:], axis=1) - ppub[:-1].max(axis=1))[skip:]),
+            "last_rows_done->first_tile_next(med cta)": med((np.median(first[1:], axis=1) - last_rows[:-1])[skip:]),
+        },
+    }
+    busy = (rowsd - first)[sl]
+    out["cta_M_us_p5_p50_p95_max"] = [us(np.percentile(np.median(busy, axis=0), q)) for q in (5, 50, 95, 100)]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", action="append", default=[])
@@ -153,7 +189,10 @@ def main():
                    "rank": rank, "opts": opts, "variant": cgb.gemv_variants()[ctx.get_option("gemv_variant")],
                    "rows": int(lay.rows), "n": n, "untraced_us_per_iter": best * 1e3,
                    "traced_us_per_iter": ms * 1e3 / max(1, info.iterations)}
-            rec.update(summarize(g, xr, p, int(lay.rows), n))
+            persistent = ctx.get_option("schedule_in_use") == 1
+            rec["schedule"] = "persistent" if persistent else "graph"
+            rec.update(summarize_persistent(g, int(lay.rows), n) if persistent
+                       else summarize(g, xr, p, int(lay.rows), n))
             if a.npz:
                 os.makedirs(a.npz, exist_ok=True)
                 tag = "%s_%s_r%d_%s" % (case.replace(":", "w"), rec["mode"], rank,

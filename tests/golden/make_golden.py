@@ -5,9 +5,13 @@ The reference ships no tests or golden vectors, so the pin
 outputs of its own unmodified sources (/root/reference/code/MPI/*.cc, compiled by
 oracle/Makefile into oracle/_ref/ against the stand-in mpi.h/cblas.h) with a real
 OpenBLAS 0.3.15 behind cblas_* ("openblas") and with plain left-to-right loops ("naive").
-Run from the repo root:   python tests/golden/make_golden.py [--full | --ranks]
+Run from the repo root:   python tests/golden/make_golden.py [--full | --ranks | --weak]
 (--full adds BASELINE.json's full-size configs: N=20000 to convergence and N=40000 x 200
 iterations, OpenBLAS provider only; ~2 minutes and 13 GB of host memory.)
+(--weak adds BASELINE.json configs[3], the weak-scaling ladder N = 20000 sqrt(G) x 200 iterations,
+for the sizes the reference can run: N = 20000 (G=1) and N = 28284 (G=2, 6.4 GB); G=4 is the
+N=40000 fixture of --full; G=8, N = 56568, overflows the reference's `int` index i*m_n+j
+(matrix.hh:17) -- no reference run exists for it.)
 (--ranks adds multi-rank runs of the reference: P = 2, 4, 8 ranks forked on this host by
 oracle/ref_shim/mpi_fork.cc -- the reference's own iteration count depends on P.)
 Needs /root/reference (to build oracle/_ref); the produced fixtures are committed so the
@@ -94,6 +98,11 @@ def main():
         for n, ranks in [(4096, 2), (4096, 4), (4096, 8), (2048, 2), (1000, 3)]:
             runs = {"openblas": run_ref_ranks(n, ranks)}
             save(f"ranks_n{n}_p{ranks}", dict(n=n, max_iter=n, kind="generate_lap2d", ranks=ranks), runs)
+        return
+    if "--weak" in sys.argv:
+        for n, max_iter in [(20000, 200), (28284, 200)]:
+            runs = {"openblas": run_ref([gen, str(n)], "openblas", [str(max_iter)])}
+            save(f"full_n{n}_it{max_iter}", dict(n=n, max_iter=max_iter, kind="generate_lap2d"), runs)
         return
     if "--full" in sys.argv:
         for n, max_iter in [(20000, None), (40000, 200)]:

@@ -64,8 +64,10 @@ def main():
     ctx.generate_lap2d()
     ctx.set_rhs(cgb.init_source_term(n))
     summary = {"nblk": ctx.layout().nblk}
-    for mode, opt in (("nccl", 0), ("fused", 1)):
+    for mode, opt, sched in (("nccl", 0, 0), ("fused", 1, 0), ("persistent", 1, 1)):
         ctx.set_option("exchange", opt)
+        ctx.set_option("schedule", sched)
+        assert ctx.get_option("schedule_in_use") == sched
         x = np.zeros(n)
         info, hist = ctx.solve(x, max_iter=a.max_iter, tol=1e-10, history=True)
         digest = hashlib.sha256(x.tobytes() + hist.tobytes()).hexdigest()

@@ -42,6 +42,16 @@ def test_partition_is_the_reference_rule(cgb, O):
         cgb.partition(10, 0)
 
 
+@pytest.mark.parametrize("n", [1, 2, 100, 4096, 20000, 56568])
+def test_init_source_term_bitwise_vs_oracle(cgb, O, n):
+    """cgb_init_source_term (the one entry point that needs no GPU: a host libm loop like the
+    reference's, cg.cc:218-234) == the oracle's restatement, bit for bit, incl. h != 1/n."""
+    assert np.array_equal(cgb.init_source_term(n), O.init_source_term(n))
+    assert np.array_equal(cgb.init_source_term(n, 0.37 / n), O.init_source_term(n, 0.37 / n))
+    b = cgb.init_source_term(n)
+    assert b[0] == 0.0 and np.all(b <= 0.0)
+
+
 def test_no_cpu_fallback(cgb):
     """Without a CUDA device every compute entry point returns an error; nothing is computed
     on the host."""

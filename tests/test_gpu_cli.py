@@ -103,3 +103,50 @@ def test_multi_gpu_cli_psize_column(O, tmp_path, cgb):
         ref = O.solve(O.generate_lap2d(2048), O.init_source_term(2048), max_iter=150, nranks=2, nblk=148)
         assert _step_line(r.stdout) == O.debug_line(150, ref.rsold, ref.norm_x, ref.rel_resid)
     assert [row.split(",")[:2] for row in out.read_text().splitlines()] == [["2048", "2"]] * 2
+
+
+# --------------------------------------------------------------------------- INTEGRATION.md section B, compiled
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+REF_CGB = os.path.join(REF_DIR, "cgsolver_ref_cgb")   # the reference's main + reader + rest of cg.cc, solve -> libcgb200
+REF_CPU = os.path.join(REF_DIR, "cgsolver_ref")       # the unmodified reference (CPU, OpenBLAS or naive loops)
+
+
+def _run_ref(exe, args, np_ranks=1, timeout=600):
+    env = dict(os.environ, CGREF_NP=str(np_ranks), CGREF_BLAS="auto", OPENBLAS_NUM_THREADS="8", OMP_NUM_THREADS="8")
+    return subprocess.run([exe] + args, capture_output=True, text=True, timeout=timeout, env=env)
+
+
+@pytest.mark.parametrize("ranks", [1, 2])
+def test_reference_main_bound_to_libcgb200(O, cgb, tmp_path, ranks):
+    """The binding stub of INTEGRATION.md B (oracle/ref_shim/cg_cgb.cc) under the reference's OWN,
+    unmodified cg_main.cc / matrix / rest of cg.cc (oracle/Makefile: cgsolver_ref_cgb; fork shim for
+    P = 2, one rank per GPU): stdout and the results row against the unmodified CPU program
+    (cgsolver_ref) on the same command line -- and, digit for digit, against the oracle."""
+    if not (os.path.exists(REF_CGB) and os.path.exists(REF_CPU)):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    if cgb.device_count() < ranks:
+        pytest.skip("needs %d GPUs" % ranks)
+    n, cap = 1448, "200"
+    out_gpu, out_cpu = tmp_path / "gpu.txt", tmp_path / "cpu.txt"
+    g = _run_ref(REF_CGB, [str(n), str(out_gpu), cap], np_ranks=ranks)
+    assert g.returncode == 0, g.stdout + g.stderr
+    c = _run_ref(REF_CPU, [str(n), str(out_cpu), cap])
+    assert c.returncode == 0, c.stderr
+    lg, lc = _step_line(g.stdout), _step_line(c.stdout)
+    mg, mc = LINE.match(lg), LINE.match(lc)
+    assert mg and mc, (lg, lc)
+    assert mg.group(1) == mc.group(1) == "200"                       # [STEP k]
+    for i in (2, 3, 4):                                              # residual, ||x||, ||Ax-b||/||b||
+        a, b = float(mg.group(i)), float(mc.group(i))
+        assert abs(a - b) <= 2e-6 * abs(b), (i, lg, lc)              # 7 printed digits; orders differ in the last
+    ref = O.solve(O.generate_lap2d(n), O.init_source_term(n), max_iter=200, nranks=ranks, nblk=148)
+    assert lg == O.debug_line(200, ref.rsold, ref.norm_x, ref.rel_resid)
+    rg, rc = out_gpu.read_text().split(","), out_cpu.read_text().split(",")
+    assert rg[:2] == [str(n), str(ranks)] and rc[:2] == [str(n), "1"]   # n,psize,seconds (cg_main.cc:62)
+    assert 0 < float(rg[2]) < 120
+    # converged run: the iteration count the reference prints, within +-1
+    g = _run_ref(REF_CGB, ["1024", str(out_gpu)], np_ranks=ranks)
+    c = _run_ref(REF_CPU, ["1024", str(out_cpu)])
+    assert g.returncode == 0 and c.returncode == 0, g.stderr + c.stderr
+    kg, kc = int(LINE.match(_step_line(g.stdout)).group(1)), int(LINE.match(_step_line(c.stdout)).group(1))
+    assert abs(kg - kc) <= 1, (kg, kc)

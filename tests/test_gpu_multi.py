@@ -47,7 +47,7 @@ def _run_ranks(G, fn):
     return out
 
 
-def _solve_sharded(cgb, O, n, G, max_iter, exchange, setup=None, variant=None):
+def _solve_sharded(cgb, O, n, G, max_iter, exchange, setup=None, variant=None, schedule=None):
     b = O.init_source_term(n)
     ctxs = [cgb.Context(n, r, G, r) for r in range(G)]
     try:
@@ -59,6 +59,11 @@ def _solve_sharded(cgb, O, n, G, max_iter, exchange, setup=None, variant=None):
             c.set_option("exchange", exchange)
             if variant is not None:
                 c.set_option("gemv_variant", variant)
+            if schedule is not None:
+                c.set_option("schedule", schedule)
+        in_use = ctxs[0].get_option("schedule_in_use")
+        if schedule is not None and exchange == 1:
+            assert in_use == schedule, "the requested schedule is not the one in use"
 
         def rank_body(r):
             c = ctxs[r]
@@ -80,13 +85,19 @@ def _solve_sharded(cgb, O, n, G, max_iter, exchange, setup=None, variant=None):
     return res, nblk, b
 
 
-@pytest.mark.parametrize("exchange", [0, 1], ids=["nccl", "fused"])
+# (exchange, schedule): ncclAllGather between the kernels of a graph; the exchange fused into the
+# mat-vec kernel of the graph; the persistent kernel (whole loop in one launch, csrc/persist.cu)
+MODES = {"nccl": (0, 0), "fused-graph": (1, 0), "fused-persistent": (1, 1)}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("n,max_iter", [(1024, 1024), (1001, 120), (2050, 200)])
-def test_two_gpu_solve_bitwise_vs_emulated_ranks(cgb, O, n, max_iter, exchange):
+def test_two_gpu_solve_bitwise_vs_emulated_ranks(cgb, O, n, max_iter, mode):
     if _ngpu(cgb) < 2:
         pytest.skip("needs 2 GPUs")
     G = 2
-    res, nblk, b = _solve_sharded(cgb, O, n, G, max_iter, exchange)
+    exchange, schedule = MODES[mode]
+    res, nblk, b = _solve_sharded(cgb, O, n, G, max_iter, exchange, schedule=schedule)
     ref = O.solve(O.generate_lap2d(n), b, max_iter=max_iter, nranks=G, nblk=nblk)
     for r, (x, info, hist, nx, rr) in enumerate(res):
         assert info.k == ref.k and bool(info.converged) == ref.converged, r
@@ -95,8 +106,8 @@ def test_two_gpu_solve_bitwise_vs_emulated_ranks(cgb, O, n, max_iter, exchange):
         assert nx == ref.norm_x and rr == ref.rel_resid, r
 
 
-@pytest.mark.parametrize("exchange", [0, 1], ids=["nccl", "fused"])
-def test_all_gpus_match_the_reference(cgb, O, golden_dir, exchange):
+@pytest.mark.parametrize("mode", list(MODES))
+def test_all_gpus_match_the_reference(cgb, O, golden_dir, mode):
     """G = every GPU on the box against the UNMODIFIED reference: its 1-rank run and, when a
     fixture exists (P = 2, 4, 8), its own P = G rank run (forked MPI ranks, ranks_n4096_pG.npz).
     Residual norms 1e-10 before the rounding floor, x 1e-9; the iteration count within +-1 of a
@@ -109,7 +120,8 @@ def test_all_gpus_match_the_reference(cgb, O, golden_dir, exchange):
     g1 = np.load(os.path.join(golden_dir, "gen_n4096.npz"))
     n = int(g1["n"])
     ks = reference_k_set(golden_dir, g1)
-    res, nblk, b = _solve_sharded(cgb, O, n, G, n, exchange)
+    exchange, schedule = MODES[mode]
+    res, nblk, b = _solve_sharded(cgb, O, n, G, n, exchange, schedule=schedule)
     fixtures = [g1]
     pg = os.path.join(golden_dir, "ranks_n4096_p%d.npz" % G)
     if os.path.exists(pg):
@@ -178,7 +190,7 @@ def test_torchrun_two_ranks(cgb, O, tmp_path):
     n = 1536
     b = O.init_source_term(n)
     ref = O.solve(O.generate_lap2d(n), b, max_iter=150, nranks=2, nblk=got["nblk"])
-    for mode in ("nccl", "fused"):
+    for mode in ("nccl", "fused", "persistent"):
         assert got[mode]["k"] == ref.k
         assert np.array_equal(np.array(got[mode]["hist"]), ref.hist), mode
         assert np.array_equal(np.array(got[mode]["x"]), ref.x), mode
