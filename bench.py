@@ -287,6 +287,7 @@ def product_arm(args):
     tuned = None
     if args.variant is None and not args.no_autotune:
         tuned = ctx.autotune()                    # one-off shape selection, outside every timed region
+        barrier()
     lay = ctx.layout()
     persistent = ctx.get_option("schedule_in_use") == 1
     variant_name = cgb.gemv_variants()[ctx.get_option("gemv_variant")]

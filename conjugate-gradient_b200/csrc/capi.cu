@@ -1395,7 +1395,21 @@ extern "C" int cgb_autotune(cgb_ctx *c, int iters, int *chosen, float *us_per_it
     const bool want_persist = c->opt_schedule == 1 && !c->opt_compat && !(c->world > 1 && keep_exchange == 0 && c->comm);
     Ctl ctl0;
     CK(cudaMemcpy(&ctl0, c->ctl, sizeof ctl0, cudaMemcpyDeviceToHost));
-    if (c->world > 1) { // tune alone: every peer pointer aims at the own buffer
+    // Tune alone, on SCRATCH gather buffers: every peer pointer aims at the scratch copy, so the
+    // real buffers -- which a peer that has already left its own tuning may be writing -- stay untouched
+    uint4 *const real_ll = c->ll, *const real_rr = c->rr_ll;
+    uint4 *tune_ll = nullptr, *tune_rr = nullptr;
+    CK(cudaMalloc(&tune_ll, c->ll_bytes));
+    if (cudaMalloc(&tune_rr, (size_t)2 * c->nchunks * sizeof(uint4)) != cudaSuccess) {
+        cudaFree(tune_ll);
+        return fail(CGB_ERR_NOMEM, "autotune scratch");
+    }
+    cudaMemsetAsync(tune_ll, 0, c->ll_bytes, c->stream);
+    cudaMemsetAsync(tune_rr, 0, (size_t)2 * c->nchunks * sizeof(uint4), c->stream);
+    c->ll = tune_ll;
+    c->rr_ll = tune_rr;
+    c->peer_ll[c->rank] = tune_ll;
+    if (c->world > 1) {
         c->opt_loopback = 1;
         c->p2p_ready = true;
         c->opt_exchange = 1;
@@ -1442,7 +1456,13 @@ extern "C" int cgb_autotune(cgb_ctx *c, int iters, int *chosen, float *us_per_it
     }
     // a candidate must beat the configured shape by more than the run-to-run noise
     if (default_us > 0.f && best_us > default_us * 0.997f) best = keep_variant;
-    // leave no trace: state, exchange epoch and the LL entries written by the looped-back runs
+    // leave no trace: state, exchange epoch; the LL entries of the looped-back runs go with the scratch
+    cudaStreamSynchronize(c->stream);
+    c->ll = real_ll;
+    c->rr_ll = real_rr;
+    c->peer_ll[c->rank] = real_ll;
+    cudaFree(tune_ll);
+    cudaFree(tune_rr);
     c->opt_loopback = keep_loopback;
     c->p2p_ready = keep_ready;
     c->opt_exchange = keep_exchange;
@@ -1453,8 +1473,6 @@ extern "C" int cgb_autotune(cgb_ctx *c, int iters, int *chosen, float *us_per_it
     gemv_variant(best).preload();
     if (persist_index(c) >= 0) persist_variant(persist_index(c)).preload();
     CK(cudaMemcpyAsync(c->ctl, &ctl0, sizeof ctl0, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(c->ll, 0, c->ll_bytes, c->stream));
-    CK(cudaMemsetAsync(c->rr_ll, 0, (size_t)2 * c->nchunks * sizeof(uint4), c->stream));
     CK(cudaMemsetAsync(c->st, 0, sizeof(State), c->stream));
     *c->h_done = 0;
     CK(cudaStreamSynchronize(c->stream));

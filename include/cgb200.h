@@ -143,7 +143,7 @@ const char *cgb_gemv_variant_name(int variant);
  * resident matrix, the fastest becomes the configured variant.  Call it after the matrix is
  * set and OUTSIDE any timed region (the reference's timer brackets solve() only,
  * code/MPI/cg_main.cc:53-55).  A rank of world > 1 tunes alone (its exchange looped back to
- * itself); peers must not be inside a solve meanwhile.  All shapes share one summation order:
+ * itself on scratch buffers); peers need not take part or wait.  All shapes share one summation order:
  * the choice never changes a result bit.  us_per_iter (nullable, cgb_gemv_variant_count()
  * floats) receives the time of every candidate, < 0 for shapes that were not candidates. */
 int cgb_autotune(cgb_ctx *ctx, int iters, int *chosen, float *us_per_iter);
