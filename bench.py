@@ -473,7 +473,7 @@ def product_arm(args):
     cfg = base_config(args.workload, n, world, iters)
     cfg.update({"gemv_variant": variant_name, "nblk": lay.nblk,
                 "schedule": ("persistent cooperative kernel (1 launch per step)" if persistent
-                             else "CUDA graph of 3 kernels per iteration"),
+                             else "CUDA graph of 4 kernels per iteration"),
                 "autotune": tuned, "options": ctx_opts(args), "parallelism": "rows%d" % world,
                 "exchange": exchange_name})
     line = {

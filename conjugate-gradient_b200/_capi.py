@@ -259,7 +259,7 @@ class Context:
     def gemv(self, v: np.ndarray, want_partials: bool = False):
         lay = self.layout()
         y = np.empty(lay.rows, dtype=np.float64)
-        bp = np.empty(lay.nblk, dtype=np.float64) if want_partials else None
+        bp = np.empty(lay.nchunks, dtype=np.float64) if want_partials else None   # chunk partials of v.(A v)
         pap = C.c_double()
         v = np.ascontiguousarray(v, dtype=np.float64)
         _check(self._lib.cgb_gemv(self._h, _p(v), _p(y), _p(bp), C.byref(pap)))

@@ -117,7 +117,8 @@ struct cgb_ctx {
     double *compat_part = nullptr; // chunk partials of the compat mat-vec
     size_t compat_part_cap = 0;
     int poll_every = 16, graph_unroll = 16, opt_pdl = 1, opt_l2_prefetch = 4;
-    int opt_l2_prefetch_mode = 0;  // persistent kernel: 0 = bulk prefetch (TMA), 1 = prefetch.global.L2 lines
+    int opt_balance = 1;           // persistent kernel: re-balance the rows between the CTAs from measured speeds
+    long long aux_stride = 0;      // entries of one parity of the local LL side buffer
     int opt_schedule = 1;          // 1: persistent cooperative kernel (persist.cu) when usable, 0: graph of 3 kernels
     long long spin_timeout_ms = 20000; // bound of the device-side waits on other CTAs / ranks
     PersistSync *psync = nullptr;
@@ -132,7 +133,7 @@ struct cgb_ctx {
     int trace_cap = 0;
 
     double *A = nullptr, *p = nullptr, *r = nullptr, *x = nullptr, *b = nullptr;
-    double *apx = nullptr, *rrpart = nullptr, *scratch = nullptr, *hist = nullptr, *sink = nullptr;
+    double *apx = nullptr, *rrpart = nullptr, *papart = nullptr, *scratch = nullptr, *hist = nullptr, *sink = nullptr;
     // apx: plain gather buffer [world][slot_cap] doubles.  ll: fused-mode LL buffers
     // [2][world][slot_cap] x 16 B, the allocation peers map; ctl: local control words.
     long long bufstride = 0;
@@ -239,6 +240,7 @@ VecArgs make_vec_args(const cgb_ctx *c)
     a.b = c->b;
     a.apx = c->apx;
     a.rrpart = c->rrpart;
+    a.papart = c->papart;
     a.st = c->st;
     a.host_done = c->d_hdone;
     a.hist = c->hist;
@@ -257,7 +259,7 @@ void set_variant(cgb_ctx *c, int v)
 {
     c->variant = v;
     c->nblk = c->sm_count * gemv_variant(v).ctas_per_sm;
-    c->slot = (c->maxrows + c->nblk + 1) & ~1LL;
+    c->slot = (c->maxrows + 1) & ~1LL;
 }
 
 void free_trace(cgb_ctx *c)
@@ -313,9 +315,10 @@ int launch_iteration(cgb_ctx *c)
     if (rc) return rc;
     if ((rc = launch_gather(c))) return rc;                                 // cg.cc:135-136 (moved)
     const VecArgs va = make_vec_args(c);
-    CK(launch_update_xr(va, c->stream));                                    // cg.cc:105-117
+    CK(launch_pap_partials(va, c->stream));                                 // cg.cc:105
+    CK(launch_update_xr(va, c->stream));                                    // cg.cc:106-117
     CK(launch_update_p(va, c->stream));                                     // cg.cc:120-132
-    c->kernel_launches += 2;
+    c->kernel_launches += 3;
     return CGB_OK;
 }
 
@@ -354,10 +357,8 @@ int persist_index(const cgb_ctx *c)
 
 void persist_scratch(const cgb_ctx *c, int *qs_n, int *scr_n)
 {
-    const long long rpc = (c->rows + c->nblk - 1) / c->nblk;
-    long long scr = (long long)c->world * c->nblk;
-    if (c->nchunks > scr) scr = c->nchunks;
-    *qs_n = (int)((rpc + 1) & ~1LL);
+    const long long scr = c->nchunks > c->nblk ? c->nchunks : c->nblk; // chunk partials / per-CTA timings
+    *qs_n = 0;
     *scr_n = (int)((scr + 1) & ~1LL);
 }
 
@@ -373,7 +374,7 @@ const char *persist_unusable(const cgb_ctx *c)
     if (c->nchunks > (long long)persist_max_chunks() * c->nblk) return "N too large for the per-CTA vector chunks";
     int qs_n, scr_n;
     persist_scratch(c, &qs_n, &scr_n);
-    if (persist_variant(pi).smem_fixed() + (size_t)(qs_n + scr_n) * 8 + 256 > (size_t)c->smem_optin)
+    if (persist_variant(pi).smem_fixed() + (size_t)(qs_n + scr_n) * 8 + 4096 > (size_t)c->smem_optin) // + static
         return "tile ring + scratch exceed shared memory";
     return nullptr;
 }
@@ -392,7 +393,7 @@ int launch_persist(cgb_ctx *c, long long iters)
         for (int g = 0; g < c->world; ++g) a.peer_ll[g] = c->ll + ((long long)g - c->rank) * c->slot;
     a.ll = c->ll;
     a.rr_ll = c->rr_ll;
-    a.rr_stride = c->nchunks;
+    a.rr_stride = c->aux_stride;
     a.sync = c->psync;
     a.st = c->st;
     a.ctl = c->ctl;
@@ -412,7 +413,7 @@ int launch_persist(cgb_ctx *c, long long iters)
     a.world = c->world;
     a.iters = (int)iters;
     a.l2_prefetch = c->opt_l2_prefetch;
-    a.l2_prefetch_mode = c->opt_l2_prefetch_mode;
+    a.balance = c->opt_balance;
     persist_scratch(c, &a.qs_n, &a.scr_n);
     a.tol = c->tol;
     a.spin_ns = (unsigned long long)c->spin_timeout_ms * 1000000ULL;
@@ -526,7 +527,8 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
     int max_cps = 1;
     for (int v = 0; v < gemv_variant_count(); ++v)
         if (gemv_variant(v).ctas_per_sm > max_cps) max_cps = gemv_variant(v).ctas_per_sm;
-    c->slot_cap = (c->maxrows + (long long)c->sm_count * max_cps + 1) & ~1LL;
+    c->slot_cap = (c->maxrows + 1) & ~1LL;
+    (void)max_cps;
     set_variant(c, 0);
 
     auto bail = [&](int code) {
@@ -560,13 +562,16 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
         CKB(cudaMemsetAsync(c->ll, 0, c->ll_bytes, c->stream)); // tag 0 is never used
         c->peer_ll[rank] = c->ll;
     }
-    CKB(cudaMalloc(&c->rr_ll, (size_t)2 * c->nchunks * sizeof(uint4)));
-    CKB(cudaMemsetAsync(c->rr_ll, 0, (size_t)2 * c->nchunks * sizeof(uint4), c->stream));
+    c->aux_stride = 2 * c->nchunks + 2LL * c->sm_count; // [r'r | p'Ap chunk partials | per-CTA times]
+    CKB(cudaMalloc(&c->rr_ll, (size_t)2 * c->aux_stride * sizeof(uint4)));
+    CKB(cudaMemsetAsync(c->rr_ll, 0, (size_t)2 * c->aux_stride * sizeof(uint4), c->stream));
     CKB(cudaMalloc(&c->psync, sizeof(PersistSync)));
     CKB(cudaMemsetAsync(c->psync, 0, sizeof(PersistSync), c->stream));
     CKB(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CKB(cudaMemsetAsync(c->ctl, 0, sizeof(Ctl), c->stream));
     CKB(cudaMalloc(&c->rrpart, (size_t)c->nchunks * sizeof(double)));
+    CKB(cudaMalloc(&c->papart, (size_t)c->nchunks * sizeof(double)));
+    CKB(cudaMemsetAsync(c->papart, 0, (size_t)c->nchunks * sizeof(double), c->stream));
     CKB(cudaMalloc(&c->scratch, (size_t)(3 * c->nchunks + 8) * sizeof(double)));
     CKB(cudaMalloc(&c->sink, 64));
     CKB(cudaMalloc(&c->st, sizeof(State)));
@@ -601,7 +606,7 @@ extern "C" int cgb_destroy(cgb_ctx *c)
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     for (void *p : c->ipc_opened)
         if (p) cudaIpcCloseMemHandle(p);
-    double *bufs[] = {c->A, c->p, c->r, c->x, c->b, c->apx, c->rrpart, c->scratch, c->hist, c->sink};
+    double *bufs[] = {c->A, c->p, c->r, c->x, c->b, c->apx, c->rrpart, c->papart, c->scratch, c->hist, c->sink};
     for (double *p : bufs)
         if (p) cudaFree(p);
     if (c->st) cudaFree(c->st);
@@ -903,8 +908,8 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
         if (value < 0 || value > 64) return fail(CGB_ERR_INVALID, "l2_prefetch must be in [0, 64] pipeline steps");
         c->opt_l2_prefetch = (int)value;
         drop_graph(c);
-    } else if (k == "l2_prefetch_mode") {
-        c->opt_l2_prefetch_mode = value != 0;
+    } else if (k == "balance") {
+        c->opt_balance = value != 0;
     } else if (k == "schedule") {
         if (value != 0 && value != 1) return fail(CGB_ERR_INVALID, "schedule must be 0 (graph of 3 kernels) or 1 (persistent)");
         c->opt_schedule = (int)value;
@@ -991,7 +996,7 @@ extern "C" int cgb_get_option(cgb_ctx *c, const char *key, int64_t *value)
     else if (k == "exchange") *value = c->opt_exchange;
     else if (k == "trace") *value = c->trace_cap;
     else if (k == "schedule") *value = c->opt_schedule;
-    else if (k == "l2_prefetch_mode") *value = c->opt_l2_prefetch_mode;
+    else if (k == "balance") *value = c->opt_balance;
     else if (k == "schedule_in_use") *value = (c->opt_schedule == 1 && !persist_unusable(c)) ? 1 : 0;
     else if (k == "spin_timeout_ms") *value = c->spin_timeout_ms;
     else if (k == "loopback") *value = c->opt_loopback;
@@ -1128,7 +1133,7 @@ extern "C" int cgb_iterate(cgb_ctx *c, int64_t iters, float *ms)
         while (i < batch) {
             if (graph && c->graph_exec && batch - i >= c->graph_unroll) {
                 CK(cudaGraphLaunch(c->graph_exec, c->stream));
-                c->kernel_launches += (c->opt_compat ? 4LL : 3LL) * c->graph_unroll;
+                c->kernel_launches += (c->opt_compat ? 5LL : 4LL) * c->graph_unroll;
                 i += c->graph_unroll;
             } else if (profile) {
                 const long long slot = 2 * (issued + i);
@@ -1137,9 +1142,10 @@ extern "C" int cgb_iterate(cgb_ctx *c, int64_t iters, float *ms)
                 CK(cudaEventRecord(c->prof_ev[slot + 1], c->stream));
                 if ((rc = launch_gather(c))) return rc;
                 const VecArgs va = make_vec_args(c);
+                CK(launch_pap_partials(va, c->stream));
                 CK(launch_update_xr(va, c->stream));
                 CK(launch_update_p(va, c->stream));
-                c->kernel_launches += 2;
+                c->kernel_launches += 3;
                 i += 1;
             } else {
                 if ((rc = launch_iteration(c))) return rc;
@@ -1239,7 +1245,7 @@ extern "C" int cgb_residual_check(cgb_ctx *c, double *norm_x, double *rel_resid)
 }
 
 // ------------------------------------------------------------------ kernel-level hooks
-extern "C" int cgb_gemv(cgb_ctx *c, const double *v_host, double *y_host, double *block_partials,
+extern "C" int cgb_gemv(cgb_ctx *c, const double *v_host, double *y_host, double *chunk_partials,
                         double *pAp)
 {
     int rc = use_device(c);
@@ -1256,13 +1262,12 @@ extern "C" int cgb_gemv(cgb_ctx *c, const double *v_host, double *y_host, double
     const Gather gth = make_gather(c);
     const double *mine = c->apx + (long long)c->rank * c->slot;
     if (y_host) CK(cudaMemcpyAsync(y_host, mine, (size_t)c->rows * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (block_partials)
-        CK(cudaMemcpyAsync(block_partials, mine + c->maxrows, (size_t)c->nblk * 8, cudaMemcpyDeviceToHost,
-                           c->stream));
-    if (pAp) {
+    if (chunk_partials || pAp) {
         double *out = c->scratch + 3 * c->nchunks;
-        CK(launch_sum_partials(c->apx, gth, out, c->stream));
-        c->kernel_launches += 1;
+        CK(launch_pap_plain(c->p, c->apx, gth, c->n, c->papart, out, c->stream));
+        c->kernel_launches += 2;
+        if (chunk_partials)
+            CK(cudaMemcpyAsync(chunk_partials, c->papart, (size_t)c->nchunks * 8, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync(c->h_pin, out, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
@@ -1400,12 +1405,12 @@ extern "C" int cgb_autotune(cgb_ctx *c, int iters, int *chosen, float *us_per_it
     uint4 *const real_ll = c->ll, *const real_rr = c->rr_ll;
     uint4 *tune_ll = nullptr, *tune_rr = nullptr;
     CK(cudaMalloc(&tune_ll, c->ll_bytes));
-    if (cudaMalloc(&tune_rr, (size_t)2 * c->nchunks * sizeof(uint4)) != cudaSuccess) {
+    if (cudaMalloc(&tune_rr, (size_t)2 * c->aux_stride * sizeof(uint4)) != cudaSuccess) {
         cudaFree(tune_ll);
         return fail(CGB_ERR_NOMEM, "autotune scratch");
     }
     cudaMemsetAsync(tune_ll, 0, c->ll_bytes, c->stream);
-    cudaMemsetAsync(tune_rr, 0, (size_t)2 * c->nchunks * sizeof(uint4), c->stream);
+    cudaMemsetAsync(tune_rr, 0, (size_t)2 * c->aux_stride * sizeof(uint4), c->stream);
     c->ll = tune_ll;
     c->rr_ll = tune_rr;
     c->peer_ll[c->rank] = tune_ll;
@@ -1419,7 +1424,6 @@ extern "C" int cgb_autotune(cgb_ctx *c, int iters, int *chosen, float *us_per_it
     int best = keep_variant;
     float best_us = -1.f, default_us = -1.f;
     for (int v = 0; v < nv && rc == CGB_OK; ++v) {
-        if (gemv_variant(v).ctas_per_sm != gemv_variant(keep_variant).ctas_per_sm) continue; // the grid (nblk) is part of the result's definition
         if (strncmp(gemv_variant(v).name, "tma", 3) != 0 || strstr(gemv_variant(v).name, "nohint")) continue;
         set_variant(c, v);
         const bool persist = want_persist && !persist_unusable(c);

@@ -32,7 +32,7 @@ struct Ctl {
 };
 
 // Geometry of the gathered mat-vec result: rank g owns slot g of `slot` entries,
-// [0, rows_g) = its Ap rows, [maxrows, maxrows + nblk) = its p'Ap block partials.
+// [0, rows_g) = its Ap rows.
 //   plain buffer (`apx`, doubles)  : 1 GPU, ncclAllGather mode, staging for the test hooks
 //   LL buffers (`ll`, 16 B entries): fused mode.  An entry is {lo32, tag, hi32, tag}: the value
 //       carries its own arrival flag (the tag of the exchange), so the producer needs no fence
@@ -102,7 +102,7 @@ struct PersistArgs {
     double *rrpart;            // nchunks chunk partials of r'r (also the hand-over to the next launch)
     uint4 *peer_ll[kMaxWorld]; // every rank's LL gather buffers (self included)
     const uint4 *ll;           // this rank's own LL buffers
-    uint4 *rr_ll;              // [2][rr_stride] LL entries: chunk partials of r'r (local to this GPU)
+    uint4 *rr_ll;              // [2][rr_stride] LL entries local to this GPU: [r'r | p'Ap chunk partials | CTA times]
     long long rr_stride;
     PersistSync *sync;
     State *st;
@@ -110,8 +110,8 @@ struct PersistArgs {
     double *hist;              // nullable
     int *host_done;            // mapped pinned flag: 1 = converged, < 0 = a wait timed out
     long long ld, rows, row0, n, maxrows, n_loc, slot, bufstride, slot_off, nchunks;
-    int rank, world, iters, l2_prefetch, l2_prefetch_mode;
-    int qs_n, scr_n;           // shared-memory scratch: rows per CTA, max(world * grid, nchunks)
+    int rank, world, iters, l2_prefetch, balance;
+    int qs_n, scr_n;           // shared-memory scratch: (unused), doubles for the chunk partials
     double tol;
     unsigned long long spin_ns; // bound of every cross-CTA / cross-rank wait
     Trace trace;
@@ -140,18 +140,6 @@ __device__ __forceinline__ double warp_det_sum(const double *v, long long n, int
 {
     double s = 0.0;
     for (long long t = lane; t < n; t += 32) s = __dadd_rn(s, v[t]);
-    return warp_butterfly(s);
-}
-
-// same, elements addressed through the gather layout (block partials of all ranks)
-__device__ __forceinline__ double warp_det_sum_partials(const double *apx, const Gather &g, int lane)
-{
-    double s = 0.0;
-    const int total = g.world * g.nblk;
-    for (int t = lane; t < total; t += 32) {
-        const int r = t / g.nblk, c = t - r * g.nblk;
-        s = __dadd_rn(s, apx[(long long)r * g.slot + g.maxrows + c]);
-    }
     return warp_butterfly(s);
 }
 

@@ -67,6 +67,7 @@ struct VecArgs {
     const double *b;
     const double *apx;       // gathered mat-vec result (see Gather)
     double *rrpart;          // nchunks chunk partials of r'r
+    double *papart;          // nchunks chunk partials of p'Ap
     State *st;
     int *host_done;          // mapped pinned flag the host polls (nullable)
     double *hist;            // nullable
@@ -78,8 +79,10 @@ struct VecArgs {
 };
 // r = b - A x0 ; p = r ; rrpart = chunk partials of r.p             (cg.cc:77-92)
 cudaError_t launch_init_residual(const VecArgs &a, cudaStream_t s);
+// chunk partials of p'Ap from the gathered rows                      (cg.cc:105)
+cudaError_t launch_pap_partials(const VecArgs &a, cudaStream_t s);
 // alpha = rsold / max(p'Ap, rsold*NEARZERO) ; x += alpha p ; r -= alpha Ap ; r'r partials
-//                                                                   (cg.cc:105-117)
+//                                                                   (cg.cc:106-117)
 cudaError_t launch_update_xr(const VecArgs &a, cudaStream_t s);
 // rsnew = sum(partials) ; stop test ; beta = rsnew/rsold ; p = r + beta p   (cg.cc:120-129)
 cudaError_t launch_update_p(const VecArgs &a, cudaStream_t s);
@@ -91,8 +94,9 @@ cudaError_t launch_debug_norms(const VecArgs &a, double *scratch /* 3*nchunks */
 // generic deterministic dot (tests): out[0] = a.b
 cudaError_t launch_dot(const double *a, const double *b, long long n, double *scratch, double *out,
                        cudaStream_t s);
-// total of the block partials of all ranks (tests): out[0] = p'Ap
-cudaError_t launch_sum_partials(const double *apx, const Gather &g, double *out, cudaStream_t s);
+// hooks: chunk partials of v.(A v) from the plain gather buffer into papart, out[0] = their det_sum
+cudaError_t launch_pap_plain(const double *v, const double *apx, const Gather &g, long long n, double *papart,
+                             double *out, cudaStream_t s);
 
 // fused mode, hooks only: consume the running exchange into the plain gather buffer `apx`
 // (the kernels of the iteration read the LL entries directly)

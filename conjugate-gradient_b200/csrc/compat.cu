@@ -49,12 +49,11 @@ __global__ void compat_matvec_kernel(const double *A, const double *v, double *p
     part[(long long)blockIdx.x * n + row] = s;
 }
 
-// Second level: rows of Ap = ordered sum of the chunk partials; then the same epilogue as the
-// product mat-vec (block partials of p'Ap over the balanced row ranges, scalar bookkeeping).
+// Second level: rows of Ap = ordered sum of the chunk partials (+ the scalar bookkeeping the
+// product mat-vec does).  p'Ap is reduced from the gathered rows like for every other mat-vec.
 __global__ void __launch_bounds__(256) compat_reduce_kernel(const GemvArgs a, const double *part,
                                                             long long nchunk)
 {
-    extern __shared__ double qs[];
     if (a.st->done) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nblk = gridDim.x, c = blockIdx.x;
@@ -65,12 +64,6 @@ __global__ void __launch_bounds__(256) compat_reduce_kernel(const GemvArgs a, co
         double y = 0.0;
         for (long long ch = 0; ch < nchunk; ++ch) y = __dadd_rn(y, part[ch * a.rows + i]);
         a.base[a.slot_off + i] = y;
-        qs[i - r0] = __dmul_rn(a.v[a.row0 + i], y);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        const double bp = warp_det_sum(qs, r1 - r0, lane);
-        if (lane == 0) a.base[a.slot_off + a.maxrows + c] = bp;
     }
 }
 
@@ -99,13 +92,7 @@ cudaError_t launch_compat_matvec(const GemvArgs &a, int nblk, int num_threads, i
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const long long rpc = (n + nblk - 1) / nblk;
-    const size_t smem = (size_t)rpc * sizeof(double);
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(compat_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    compat_reduce_kernel<<<nblk, 256, smem, s>>>(a, part, nchunk);
+    compat_reduce_kernel<<<nblk, 256, 0, s>>>(a, part, nchunk);
     return cudaGetLastError();
 }
 

@@ -15,10 +15,11 @@
 //          into an even and an odd accumulator per row, a shuffle butterfly finishes the row.
 //   ldg_*  the same order with direct streaming 128-bit global loads (no staging).
 //
-// Epilogue fusion (north star): lane 0 multiplies the finished row by p_row, the CTA reduces
-// those products deterministically into ONE block partial of p'Ap -- the first level of the
-// two-level block-then-grid reduction that replaces the reference's atomicAdd; the second
-// level (det_sum over all blocks of all ranks) runs in the prologue of the x/r update.
+// The finished rows go straight to their consumers: the gather buffer of this GPU or -- fused
+// exchange -- of EVERY rank (NVLink peer stores).  p'Ap is reduced from those rows by the x/r
+// update side as chunk partials over the GLOBAL vector (the deterministic two-level block-then-
+// grid reduction that replaces the reference's atomicAdd): no reduction depends on which CTA,
+// SM or GPU computed a row, so rows can be re-balanced freely without changing a bit.
 // Block 0 also performs the scalar bookkeeping of the previous iteration (advance_state).
 #include "cgb_device.cuh"
 #include "cgb_kernels.h"
@@ -52,7 +53,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
     double *sP = sA + (size_t)STAGES * TR * TC;                   // [STAGES][TC]
     uint64_t *full = reinterpret_cast<uint64_t *>(sP + (size_t)STAGES * TC);
     uint64_t *empty = full + STAGES;
-    double *qs = reinterpret_cast<double *>(empty + STAGES);      // [rows of this CTA]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nblk = gridDim.x, c = blockIdx.x;
@@ -159,12 +159,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
             const int nr = (int)(r0 + (long long)(b + 1) * nrows / nb - rb0);
             // rows of this warp inside the block: warp, warp + CW, ...
             const int nv = (nr > warp) ? ((nr - warp + CW - 1) / CW) : 0;
-            double acc0[RPW], acc1[RPW], prow[RPW];
+            double acc0[RPW], acc1[RPW];
 #pragma unroll
             for (int s = 0; s < RPW; ++s) {
                 acc0[s] = 0.0;
                 acc1[s] = 0.0;
-                prow[s] = (s < nv) ? a.v[a.row0 + rb0 + warp + s * CW] : 0.0;
             }
             for (int t = 0; t < ntc; ++t, ++it) {
                 const int stage = it % STAGES;
@@ -204,23 +203,19 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
             }
-            // row epilogue: butterfly, store Ap_row, stash p_row * Ap_row for the block partial
+            // row epilogue: butterfly, store Ap_row
 #pragma unroll
             for (int s = 0; s < RPW; ++s) {
                 if (s < nv) {
                     const double y = warp_butterfly(__dadd_rn(acc0[s], acc1[s])); // in every lane
                     const long long li = rb0 + warp + s * CW;
                     store_out(a, obase + li, lbase + li, tag, y, lane);
-                    if (lane == 0) qs[li - r0] = __dmul_rn(prow[s], y);
                 }
             }
         }
-        if (tid == 0) trace_stamp(rec, 5);
-        named_bar_sync(1, CW * 32);
-        if (warp == 0) {
-            const double bp = warp_det_sum(qs, nrows, lane);
-            store_out(a, obase + a.maxrows + c, lbase + a.maxrows + c, tag, bp, lane);
-            if (lane == 0) trace_stamp(rec, 6);
+        if (tid == 0) {
+            trace_stamp(rec, 5);
+            trace_stamp(rec, 6);
         }
     }
 }
@@ -229,9 +224,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
 template <int W, int RPW, int UNR>
 __global__ void __launch_bounds__(W * 32) gemv_ldg_kernel(const GemvArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *qs = reinterpret_cast<double *>(smem_raw);
-
     griddep_launch_dependents();
     griddep_wait();
     if (a.st->done) return;
@@ -286,18 +278,12 @@ __global__ void __launch_bounds__(W * 32) gemv_ldg_kernel(const GemvArgs a)
                 const double y = warp_butterfly(__dadd_rn(acc0[s], acc1[s]));
                 const long long li = rg0 + s;
                 store_out(a, obase + li, lbase + li, tag, y, lane);
-                if (lane == 0) qs[li - r0] = __dmul_rn(a.v[a.row0 + li], y);
             }
         }
     }
-    __syncthreads();
-    if (warp == 0) {
-        const double bp = warp_det_sum(qs, nrows, lane);
-        store_out(a, obase + a.maxrows + c, lbase + a.maxrows + c, tag, bp, lane);
-    }
 }
 
-// read-bandwidth ceiling: stream the shard once, keep the compiler honest with a checksum
+// read-only LDG stream over the shard (a comparison point, not a ceiling: the TMA mat-vec is faster): stream the shard once, keep the compiler honest with a checksum
 __global__ void __launch_bounds__(512) read_stream_kernel(const double *A, long long n2, double *sink)
 {
     const double2 *p = reinterpret_cast<const double2 *>(A);
@@ -326,8 +312,8 @@ namespace {
 template <int CW, int RPW, int TC, int STAGES>
 size_t tma_smem(long long rows_per_cta)
 {
-    return (size_t)STAGES * CW * RPW * TC * 8 + (size_t)STAGES * TC * 8 + 2 * STAGES * 8 +
-           (size_t)rows_per_cta * 8;
+    (void)rows_per_cta;
+    return (size_t)STAGES * CW * RPW * TC * 8 + (size_t)STAGES * TC * 8 + 2 * STAGES * 8;
 }
 
 template <int CW, int RPW, int TC, int STAGES, int MINB, int POL = 0>
@@ -359,14 +345,8 @@ cudaError_t ldg_preload()
 template <int W, int RPW, int UNR>
 cudaError_t ldg_launch(const GemvArgs &a, int nblk, cudaStream_t s)
 {
-    const long long rpc = (a.rows + nblk - 1) / nblk;
-    const size_t smem = (size_t)rpc * 8;
     auto k = gemv_ldg_kernel<W, RPW, UNR>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    return launch_kernel(k, nblk, W * 32, smem, s, a.pdl != 0, a);
+    return launch_kernel(k, nblk, W * 32, 0, s, a.pdl != 0, a);
 }
 
 const GemvVariant kVariants[] = {

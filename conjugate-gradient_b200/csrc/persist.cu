@@ -170,16 +170,46 @@ __device__ __forceinline__ void mbar_wait_ns(const PersistArgs &a, uint64_t *bar
 
 } // namespace
 
+// Geometry of one CTA's mat-vec for a given row range: balanced row blocks of at most TR rows,
+// tile width per block as wide as the stage allows (a full stage keeps the bytes in flight -- and
+// with them this SM's share of the saturated HBM stream -- independent of the rows-per-CTA ratio).
+struct Geo {
+    long long r0;
+    int nrows, nb, lo, n_hi, w_lo, w_hi, ntc_lo, ntc_hi;
+    unsigned T; // pipeline steps of the mat-vec
+};
+template <int TR, int SLOT, int PMAX>
+__device__ __forceinline__ Geo make_geo(long long r0, long long r1, long long ld)
+{
+    Geo g;
+    g.r0 = r0;
+    g.nrows = (int)(r1 - r0);
+    g.nb = (g.nrows + TR - 1) / TR;
+    g.lo = g.nb ? g.nrows / g.nb : 1; // the balanced split gives blocks of lo or lo + 1 rows
+    g.n_hi = g.nb ? g.nrows - g.lo * g.nb : 0;
+    int w = (SLOT / g.lo) & ~63;
+    g.w_lo = w > PMAX ? PMAX : w;
+    w = (SLOT / (g.lo + 1)) & ~63;
+    g.w_hi = w > PMAX ? PMAX : w;
+    g.ntc_lo = (int)((ld + g.w_lo - 1) / g.w_lo);
+    g.ntc_hi = (int)((ld + g.w_hi - 1) / g.w_hi);
+    g.T = (unsigned)(g.nb - g.n_hi) * (unsigned)g.ntc_lo + (unsigned)g.n_hi * (unsigned)g.ntc_hi;
+    return g;
+}
+
+constexpr int kMaxGrid = 160; // CTAs of the persistent grid (one per SM) the re-balancing handles
+
 template <int CW, int RPW, int TC, int STAGES, int MAXC>
 __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const PersistArgs a)
 {
     constexpr int TR = CW * RPW;            // most rows of a row block
     constexpr int SLOT = TR * TC;           // doubles of A per pipeline stage
-    constexpr int PMAX = persist_pmax(SLOT, TC);  // doubles of p per pipeline stage = widest tile
+    constexpr int PMAX = persist_pmax(SLOT, TC); // doubles of p per pipeline stage = widest tile
     constexpr int NCT = CW * 32;            // consumer threads
     constexpr int EPT = kChunk / NCT;       // elements of a 256-chunk per consumer thread
     static_assert(CW == 4 || CW == 8, "chunk256 mapping is written for 4 or 8 consumer warps");
     static_assert(TC % 64 == 0, "tile width must be a multiple of 64 doubles");
+    static_assert(STAGES <= 8, "stage metadata");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sA = reinterpret_cast<double *>(smem_raw);            // [STAGES][SLOT]
     double *sP = sA + (size_t)STAGES * SLOT;                      // [STAGES][PMAX]
@@ -187,33 +217,18 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
     uint64_t *empty = full + STAGES;
     double *wsum = reinterpret_cast<double *>(empty + STAGES);    // [MAXC][8]
     double *s_sc = wsum + MAXC * 8;                               // [4] broadcast scalars
-    double *qs = s_sc + 4;                                        // [rows of this CTA]
-    double *scr = qs + a.qs_n;                                    // [max(world * grid, nchunks)]
-    __shared__ volatile int s_stop;                               // consumers -> producer: loop left
+    double *scr = s_sc + 4;                                       // [nchunks] chunk partials being summed
+    __shared__ volatile int s_stop;          // consumers -> producer: loop left
+    __shared__ volatile int s_part_seq;      // highest iteration whose row partition is in s_bnd
+    __shared__ volatile int s_prod_geo;      // highest iteration whose row partition the producer has read
+    __shared__ int s_bnd[2][kMaxGrid + 1];   // row boundaries of all CTAs, iteration parity
+    __shared__ double s_tm[kMaxGrid];        // mat-vec-phase times of all CTAs (re-balancing)
+    __shared__ long long s_c0[8];            // per stage: first column and width of the tile in flight
+    __shared__ int s_w[8];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nblk = gridDim.x, c = blockIdx.x;
-    const long long r0 = (long long)c * a.rows / nblk;
-    const long long r1 = (long long)(c + 1) * a.rows / nblk;
-    const int nrows = (int)(r1 - r0);
-    const int nb = (nrows + TR - 1) / TR;          // row blocks, balanced below
-    // Tile width of a row block: as wide as the stage allows for its rows, so that a stage is
-    // (nearly) full whatever the rows-per-CTA ratio -- under a saturated memory system an SM's
-    // share of the HBM stream is proportional to its bytes in flight (34 rows per CTA = blocks of
-    // 11, 11, 12 rows would fill 16-row x 512 tiles to 70 % only).  Any multiple of 64 keeps the
-    // summation order.  The balanced split gives blocks of `lo` or `lo + 1` rows.
-    const int lo = nb ? nrows / nb : 1;
-    auto width_of = [&](int nr) {
-        int w = (SLOT / nr) & ~63;
-        return w > PMAX ? PMAX : w;
-    };
-    const int w_lo = width_of(lo), w_hi = width_of(lo + 1);
-    const int ntc_lo = (int)((a.ld + w_lo - 1) / w_lo), ntc_hi = (int)((a.ld + w_hi - 1) / w_hi);
-    const int n_hi = nb ? nrows - lo * nb : 0;     // blocks with lo + 1 rows
-    const unsigned T = (unsigned)(nb - n_hi) * (unsigned)ntc_lo + (unsigned)n_hi * (unsigned)ntc_hi; // steps per mat-vec
-    __shared__ long long s_c0[8]; // per stage: first column and width of the tile in flight (producer only)
-    __shared__ int s_w[8];
-    static_assert(STAGES <= 8, "stage metadata");
+    const bool balance = a.balance != 0 && nblk <= kMaxGrid;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -222,33 +237,47 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
         }
         fence_mbar_init();
         s_stop = 0;
+        s_part_seq = balance ? 1 : 0x7fffffff;
+        s_prod_geo = 0;
     }
+    if (nblk <= kMaxGrid)
+        for (int k = tid; k <= nblk; k += blockDim.x) { // static start: the balanced split of gemv.cu
+            const int bk = (int)((long long)k * a.rows / nblk);
+            s_bnd[0][k] = bk;
+            s_bnd[1][k] = bk;
+        }
     __syncthreads();
     if (a.st->done) return; // converged in an earlier launch: nothing to do (uniform)
 
     const unsigned nchunks = (unsigned)a.nchunks;
+    auto geo_of = [&](int m) {
+        if (nblk <= kMaxGrid) return make_geo<TR, SLOT, PMAX>(s_bnd[m & 1][c], s_bnd[m & 1][c + 1], a.ld);
+        return make_geo<TR, SLOT, PMAX>((long long)c * a.rows / nblk, (long long)(c + 1) * a.rows / nblk, a.ld);
+    };
 
     if (warp == CW) {
         // ================= producer: streams A, never waits for the vector phases =================
-        if (T == 0) return;
         const uint64_t pol_a = l2_policy_evict_first();
         const uint64_t pol_p = l2_policy_evict_last();
-        // cursor over the pipeline steps (row block b, column tile t), wrapping from one mat-vec
-        // into the next
+        // cursor over the pipeline steps (row block b, column tile t) of one mat-vec
         struct Cur {
             int b, t, nr, wdb, ntb;
             long long rb0;
         };
-        auto cur_block = [&](Cur &k, int b) {
+        auto cur_block = [&](Cur &k, const Geo &ge, int b) {
             k.b = b;
             k.t = 0;
-            k.rb0 = r0 + (long long)b * nrows / nb;
-            k.nr = (int)(r0 + (long long)(b + 1) * nrows / nb - k.rb0);
-            k.wdb = (k.nr == lo) ? w_lo : w_hi;
-            k.ntb = (k.nr == lo) ? ntc_lo : ntc_hi;
+            if (ge.nb == 0) {
+                k.nr = 0; k.wdb = 64; k.ntb = 1; k.rb0 = ge.r0;
+                return;
+            }
+            k.rb0 = ge.r0 + (long long)b * ge.nrows / ge.nb;
+            k.nr = (int)(ge.r0 + (long long)(b + 1) * ge.nrows / ge.nb - k.rb0);
+            k.wdb = (k.nr == ge.lo) ? ge.w_lo : ge.w_hi;
+            k.ntb = (k.nr == ge.lo) ? ge.ntc_lo : ge.ntc_hi;
         };
-        auto cur_next = [&](Cur &k) {
-            if (++k.t == k.ntb) cur_block(k, (k.b + 1 == nb) ? 0 : k.b + 1);
+        auto cur_next = [&](Cur &k, const Geo &ge) {
+            if (++k.t == k.ntb) cur_block(k, ge, (k.b + 1 >= ge.nb) ? 0 : k.b + 1);
         };
         auto issueA = [&](unsigned g, const Cur &k) {
             const long long c0 = (long long)k.t * k.wdb;
@@ -272,12 +301,13 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
         auto wait_empty = [&](unsigned g) {
             if (g >= (unsigned)STAGES) mbar_wait_ns(a, &empty[g % STAGES], ((g / STAGES) & 1u) ^ 1u);
         };
+        Geo ge = geo_of(0);
         Cur cur;
-        cur_block(cur, 0);
-        unsigned pre = 0; // steps of the coming mat-vec whose A part is already in flight
+        cur_block(cur, ge, 0);
+        unsigned gbase = 0; // global step index of the first tile of mat-vec m
+        unsigned pre = 0;   // steps of the coming mat-vec whose A part is already in flight
         for (int m = 0; m < a.iters; ++m) {
-            const unsigned base = (unsigned)m * T;
-            if (m > 0) {
+            if (m > 0 && (ge.T > 0 || pre > 0)) {
                 // p of this mat-vec is final once every chunk owner has published it -- or the
                 // loop was left (converged): then only the copies in flight must still land
                 int stop = 0;
@@ -295,41 +325,54 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                 }
                 stop = __shfl_sync(0xffffffffu, stop, 0);
                 if (stop) {
-                    for (unsigned u = 0; u < pre; ++u) issueP(base + u);
-                    for (unsigned u = 0; u < pre; ++u) mbar_wait_ns(a, &full[(base + u) % STAGES], ((base + u) / STAGES) & 1u);
+                    for (unsigned u = 0; u < pre; ++u) issueP(gbase + u);
+                    for (unsigned u = 0; u < pre; ++u) mbar_wait_ns(a, &full[(gbase + u) % STAGES], ((gbase + u) / STAGES) & 1u);
                     return;
                 }
             }
-            for (unsigned u = 0; u < pre; ++u) issueP(base + u);
-            for (unsigned g = base + pre; g < base + T; ++g) {
+            for (unsigned u = 0; u < pre; ++u) issueP(gbase + u);
+            for (unsigned g = gbase + pre; g < gbase + ge.T; ++g) {
                 wait_empty(g);
                 issueA(g, cur);
-                cur_next(cur);
+                cur_next(cur, ge);
                 issueP(g);
             }
+            gbase += ge.T;
             pre = 0;
             if (m + 1 < a.iters) {
-                // run ahead into the next mat-vec: A tiles into the ring as its stages drain (A
-                // never changes), while the vector phases of this iteration run
-                const unsigned npre = T < (unsigned)STAGES ? T : (unsigned)STAGES;
-                for (; pre < npre; ++pre) {
-                    wait_empty(base + T + pre);
-                    issueA(base + T + pre, cur);
-                    cur_next(cur);
+                // the row range of the next mat-vec (re-balanced two iterations ago) ...
+                if (lane == 0) {
+                    const unsigned long long t0 = globaltimer_ns();
+                    while (s_part_seq < m + 1 && !s_stop) {
+                        __nanosleep(64);
+                        if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 6);
+                    }
                 }
-                Cur pf = cur; // ... and the steps after them into L2
-                for (int u = 0; u < a.l2_prefetch && (unsigned)u + pre < T; ++u) {
+                __syncwarp();
+                __threadfence_block();
+                if (s_stop) return; // nothing in flight: all steps of mat-vec m were consumed or the loop never reached it
+                ge = geo_of(m + 1);
+                cur_block(cur, ge, 0);
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    s_prod_geo = m + 1; // its slot may be re-used for mat-vec m + 3 from now on
+                }
+                // ... run ahead into it: A tiles into the ring as its stages drain (A never changes),
+                // the steps after them into L2, while the vector phases of this iteration run
+                const unsigned npre = ge.T < (unsigned)STAGES ? ge.T : (unsigned)STAGES;
+                for (; pre < npre; ++pre) {
+                    wait_empty(gbase + pre);
+                    issueA(gbase + pre, cur);
+                    cur_next(cur, ge);
+                }
+                Cur pf = cur;
+                for (int u = 0; u < a.l2_prefetch && (unsigned)u + pre < ge.T; ++u) {
                     const long long c0 = (long long)pf.t * pf.wdb;
                     const int w = (int)((a.ld - c0 < pf.wdb) ? (a.ld - c0) : pf.wdb);
-                    if (a.l2_prefetch_mode == 0) {
-                        for (int j = lane; j < pf.nr; j += 32)
-                            bulk_prefetch_l2(a.A + (pf.rb0 + j) * a.ld + c0, (unsigned)(w * 8));
-                    } else { // one 128-byte line per lane and instruction
-                        for (int j = 0; j < pf.nr; ++j)
-                            for (int q = lane * 16; q < w; q += 32 * 16)
-                                prefetch_l2_line(a.A + (pf.rb0 + j) * a.ld + c0 + q);
-                    }
-                    cur_next(pf);
+                    for (int j = lane; j < pf.nr; j += 32)
+                        bulk_prefetch_l2(a.A + (pf.rb0 + j) * a.ld + c0, (unsigned)(w * 8));
+                    cur_next(pf, ge);
                 }
             }
         }
@@ -364,7 +407,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
     for (unsigned t = tid; t < nchunks; t += NCT) scr[t] = a.rrpart[t];
     named_bar_sync(1, NCT);
     if (warp == 0) {
-        const double s = warp_det_sum(scr, nchunks, lane);
+        const double s = warp_det_sum_smem(scr, (int)nchunks, lane);
         if (lane == 0) {
             s_sc[0] = s;
             if (c == 0 && it0 >= 0 && a.hist) a.hist[it0] = s;
@@ -375,33 +418,97 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
     double rsnew = rsold, alpha = 0.0, conj = 0.0;
     int converged = 0, executed = 0;
 
+    // chunk256 of one value per owned element: butterfly inside the 32-groups, group g + group g + 4
+    // inside the thread (CW == 4), the rest of the perfect tree across the warps by warp 0, which
+    // publishes every partial as a self-flagging LL entry (no fence, no counter) -- and, for r'r,
+    // also plainly in rrpart for the hand-over to the next launch.
+    auto publish_chunk_partials = [&](const double (&val)[MAXC][EPT], uint4 *dst_ll, unsigned tag, double *plain) {
+#pragma unroll
+        for (int cc = 0; cc < MAXC; ++cc) {
+            double v = 0.0;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const double bf = warp_butterfly(val[cc][e]);
+                v = (e == 0) ? bf : __dadd_rn(v, bf);
+            }
+            if (lane == 0) wsum[cc * 8 + warp] = v;
+        }
+        named_bar_sync(1, NCT);
+        if (warp == 0) {
+#pragma unroll
+            for (int cc = 0; cc < MAXC; ++cc) {
+                const long long j = (long long)c + (long long)cc * nblk;
+                if (j < a.nchunks) {
+                    double t = (lane < CW) ? wsum[cc * 8 + lane] : 0.0;
+                    if (CW == 8) t = __dadd_rn(t, shfl_xor_f64(t, 4));
+                    t = __dadd_rn(t, shfl_xor_f64(t, 2));
+                    t = __dadd_rn(t, shfl_xor_f64(t, 1));
+                    if (lane == 0) {
+                        ll_store(dst_ll + j, t, tag);
+                        if (plain) plain[j] = t;
+                    }
+                }
+            }
+        }
+        named_bar_sync(1, NCT); // wsum may be reused
+    };
+    // all chunk partials of one reduction -> their det_sum, in every consumer thread
+    auto collect_chunk_partials = [&](const uint4 *src_ll, unsigned tag, int slot_sc) {
+        constexpr int PB = 3;
+        for (unsigned t0 = tid; t0 < nchunks; t0 += PB * NCT) {
+            const uint4 *src[PB];
+            double val[PB];
+            unsigned pending = 0;
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                src[u] = src_ll + t0 + u * NCT;
+                if (t0 + u * NCT < nchunks) pending |= 1u << u;
+            }
+            ll_wait_batch<PB>(a, src, pending, tag, val);
+#pragma unroll
+            for (int u = 0; u < PB; ++u)
+                if (t0 + u * NCT < nchunks) scr[t0 + u * NCT] = val[u];
+        }
+        named_bar_sync(1, NCT);
+        if (warp == 0) {
+            const double s = warp_det_sum_smem(scr, (int)nchunks, lane);
+            if (lane == 0) s_sc[slot_sc] = s;
+        }
+        named_bar_sync(1, NCT);
+        return s_sc[slot_sc];
+    };
+
     unsigned g = 0; // pipeline step counter, never reset (mbarrier parities)
     for (int m = 0; m < a.iters; ++m) {
         const long long jloop = it0 + 1 + m;             // the reference's k of this loop body
         const unsigned tag = epoch0 + 1u + (unsigned)m;  // tag + buffer of this exchange
         const long long lbase = (long long)(tag & 1u) * a.bufstride + a.slot_off;
         const uint4 *const view = a.ll + (long long)(tag & 1u) * a.bufstride;
-        uint4 *const rrview = a.rr_ll + (long long)(tag & 1u) * a.rr_stride;
+        uint4 *const aux = a.rr_ll + (long long)(tag & 1u) * a.rr_stride; // [r'r | p'Ap | times]
+        uint4 *const rrview = aux, *const papview = aux + a.nchunks, *const tmview = aux + 2 * a.nchunks;
+        const Geo ge = geo_of(m);
+        // the two parities of the partition are re-balanced in turn, two iterations out of eight
+        const bool rebalance_now = balance && (m & 7) < 2 && m + 2 < a.iters;
         unsigned long long *rec = nullptr;
         if (trace && tid == 0) {
             rec = trace + ((size_t)((tr0 + (unsigned)m) % (unsigned)a.trace.cap) * (size_t)nblk + (size_t)c) * kTraceWords;
             rec[0] = globaltimer_ns();
-            rec[7] = (unsigned long long)smid() | ((unsigned long long)nrows << 32);
+            rec[7] = (unsigned long long)smid() | ((unsigned long long)ge.nrows << 32);
         }
 
         // ------------------------------------------------ phase M: Ap rows of this CTA (cg.cc:100-102)
-        for (int b = 0; b < nb; ++b) {
-            const long long rb0 = r0 + (long long)b * nrows / nb;
-            const int nr = (int)(r0 + (long long)(b + 1) * nrows / nb - rb0);
+        unsigned long long tm0 = 0;
+        for (int b = 0; b < ge.nb; ++b) {
+            const long long rb0 = ge.r0 + (long long)b * ge.nrows / ge.nb;
+            const int nr = (int)(ge.r0 + (long long)(b + 1) * ge.nrows / ge.nb - rb0);
             const int nv = (nr > warp) ? ((nr - warp + CW - 1) / CW) : 0;
-            const int wd = (nr == lo) ? w_lo : w_hi;
-            const int ntc = (nr == lo) ? ntc_lo : ntc_hi;
-            double acc0[RPW], acc1[RPW], prow[RPW];
+            const int wd = (nr == ge.lo) ? ge.w_lo : ge.w_hi;
+            const int ntc = (nr == ge.lo) ? ge.ntc_lo : ge.ntc_hi;
+            double acc0[RPW], acc1[RPW];
 #pragma unroll
             for (int s = 0; s < RPW; ++s) {
                 acc0[s] = 0.0;
                 acc1[s] = 0.0;
-                prow[s] = 0.0;
             }
             for (int t = 0; t < ntc; ++t, ++g) {
                 const int stage = g % STAGES;
@@ -409,13 +516,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                 const long long c0 = (long long)t * wd;
                 const int w = (int)((a.ld - c0 < wd) ? (a.ld - c0) : wd);
                 mbar_wait_ns(a, &full[stage], ph);
-                if (t == 0) {
-                    // the tile carries a p slice, so every chunk of p has been published:
-                    // p at this warp's own rows (for the p'Ap epilogue) is final too
-                    if (rec && b == 0) rec[3] = globaltimer_ns();
-#pragma unroll
-                    for (int s = 0; s < RPW; ++s)
-                        if (s < nv) prow[s] = ld_cg_f64(a.p + a.row0 + rb0 + warp + s * CW);
+                if (tid == 0 && b == 0 && t == 0) {
+                    tm0 = globaltimer_ns();
+                    if (rec) rec[3] = tm0;
                 }
                 const double2 *sa2 = reinterpret_cast<const double2 *>(sA + (size_t)stage * SLOT);
                 const double2 *sp2 = reinterpret_cast<const double2 *>(sP + (size_t)stage * PMAX);
@@ -460,60 +563,30 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
             }
-            // row epilogue: butterfly, Ap_row to every rank, p_row * Ap_row for the block partial
+            // row epilogue: butterfly, Ap_row straight to every rank (lane g -> rank g: ONE store
+            // instruction, `world` transactions in flight)
 #pragma unroll
             for (int s = 0; s < RPW; ++s) {
                 if (s < nv) {
                     const double y = warp_butterfly(__dadd_rn(acc0[s], acc1[s])); // every lane holds y
                     const long long li = rb0 + warp + s * CW;
-                    // lane g stores to rank g: ONE store instruction, `world` transactions in flight
-                    // (a loop in one lane would serialise the strong.sys stores, ~0.35 us each)
                     if (lane < a.world) ll_store(a.peer_ll[lane] + lbase + li, y, tag);
-                    if (lane == 0) qs[li - r0] = __dmul_rn(prow[s], y);
                 }
             }
         }
-        named_bar_sync(1, NCT);
-        if (warp == 0) {
-            const double bp = warp_det_sum(qs, nrows, lane); // level 1 of p'Ap (cg.cc:105)
-            if (lane < a.world) ll_store(a.peer_ll[lane] + lbase + a.maxrows + c, bp, tag);
-            if (lane == 0 && rec) rec[5] = globaltimer_ns();
+        if (rebalance_now || trace) { // uniform over the CTA
+            named_bar_sync(1, NCT); // all rows of this CTA are stored
+            if (tid == 0) {
+                const unsigned long long t1 = globaltimer_ns();
+                if (rec) rec[5] = t1;
+                // the time this CTA streamed its rows in: the input of the re-balancing
+                if (rebalance_now) ll_store(tmview + c, ge.nrows > 0 ? (double)(t1 - tm0) : 0.0, tag);
+            }
         }
 
-        // ------------------------------------------------ phase U: alpha, x, r, r'r partials (cg.cc:105-116)
-        {
-            // every block partial of every rank: polled straight from the LL entries, 5 in flight
-            const int total = a.world * nblk;
-            constexpr int PB = 5;
-            for (int t0 = tid; t0 < total; t0 += PB * NCT) {
-                const uint4 *src[PB];
-                double val[PB];
-                unsigned pending = 0;
-#pragma unroll
-                for (int u = 0; u < PB; ++u) {
-                    const int t = t0 + u * NCT;
-                    const int rk = t / nblk, cb = t - rk * nblk;
-                    src[u] = view + (long long)rk * a.slot + a.maxrows + cb;
-                    if (t < total) pending |= 1u << u;
-                }
-                ll_wait_batch<PB>(a, src, pending, tag, val);
-#pragma unroll
-                for (int u = 0; u < PB; ++u)
-                    if (t0 + u * NCT < total) scr[t0 + u * NCT] = val[u];
-            }
-            named_bar_sync(1, NCT);
-            if (warp == 0) {
-                const double cj = warp_det_sum_smem(scr, total, lane);            // p'Ap, every rank's blocks
-                const double clamp = __dmul_rn(rsold, kNearZero);
-                const double al = __ddiv_rn(rsold, (cj < clamp) ? clamp : cj);    // cg.cc:107
-                if (lane == 0) {
-                    s_sc[1] = al;
-                    s_sc[3] = cj;
-                }
-            }
-        }
-        // the Ap values of the own chunks (all block partials are in, so these rows are too --
-        // up to reordering of a peer's stores, which the entries' own flags cover)
+        // ------------------------------------------------ phase U: p'Ap, alpha, x, r, r'r (cg.cc:105-116)
+        // The Ap values of the own chunks, polled straight from the LL entries the owning CTAs (of
+        // any rank) stored; they serve both p'Ap and the r update.
         double apv[MAXC * EPT];
         {
             const uint4 *esrc[MAXC * EPT];
@@ -531,75 +604,136 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
             }
             ll_wait_batch<MAXC * EPT>(a, esrc, pending, tag, apv);
         }
-        named_bar_sync(1, NCT);
-        alpha = s_sc[1];
-        conj = s_sc[3];
-        if (rec) rec[1] = globaltimer_ns();
+        {
+            double q[MAXC][EPT];
 #pragma unroll
-        for (int cc = 0; cc < MAXC; ++cc) {
-            const long long j = (long long)c + (long long)cc * nblk;
-            double v = 0.0;
+            for (int cc = 0; cc < MAXC; ++cc)
 #pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                const long long i = j * kChunk + tid + e * NCT;
-                double sq = 0.0;
-                if (j < a.nchunks && i < a.n) {
-                    const double ap = apv[cc * EPT + e];
-                    xs[cc][e] = __fma_rn(alpha, ps[cc][e], xs[cc][e]);   // cg.cc:110
-                    rs[cc][e] = __fma_rn(-alpha, ap, rs[cc][e]);        // cg.cc:113
-                    sq = __dmul_rn(rs[cc][e], rs[cc][e]);               // cg.cc:116
+                for (int e = 0; e < EPT; ++e) {
+                    const long long j = (long long)c + (long long)cc * nblk;
+                    const long long i = j * kChunk + tid + e * NCT;
+                    q[cc][e] = (j < a.nchunks && i < a.n) ? __dmul_rn(ps[cc][e], apv[cc * EPT + e]) : 0.0; // cg.cc:105
                 }
-                const double bf = warp_butterfly(sq);                   // 32-group warp + e * CW
-                v = (e == 0) ? bf : __dadd_rn(v, bf);                   // group g + group g + 4
-            }
-            if (lane == 0) wsum[cc * 8 + warp] = v;
+            publish_chunk_partials(q, papview, tag, nullptr);
         }
-        named_bar_sync(1, NCT);
-        if (warp == 0) {
-            // chunk256: the remaining levels of the perfect tree, across the consumer warps;
-            // the partial is PUBLISHED as a self-flagging LL entry (no fence, no counter)
+        conj = collect_chunk_partials(papview, tag, 3);                               // cg.cc:105-106
+        {
+            const double clamp = __dmul_rn(rsold, kNearZero);
+            alpha = __ddiv_rn(rsold, (conj < clamp) ? clamp : conj);                  // cg.cc:107
+        }
+        if (rec) rec[1] = globaltimer_ns();
+        {
+            double sq[MAXC][EPT];
 #pragma unroll
-            for (int cc = 0; cc < MAXC; ++cc) {
-                const long long j = (long long)c + (long long)cc * nblk;
-                if (j < a.nchunks) {
-                    double t = (lane < CW) ? wsum[cc * 8 + lane] : 0.0;
-                    if (CW == 8) t = __dadd_rn(t, shfl_xor_f64(t, 4));
-                    t = __dadd_rn(t, shfl_xor_f64(t, 2));
-                    t = __dadd_rn(t, shfl_xor_f64(t, 1));
-                    if (lane == 0) {
-                        ll_store(rrview + j, t, tag);
-                        a.rrpart[j] = t; // hand-over to the next launch / cgb_solve_end
+            for (int cc = 0; cc < MAXC; ++cc)
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const long long j = (long long)c + (long long)cc * nblk;
+                    const long long i = j * kChunk + tid + e * NCT;
+                    sq[cc][e] = 0.0;
+                    if (j < a.nchunks && i < a.n) {
+                        xs[cc][e] = __fma_rn(alpha, ps[cc][e], xs[cc][e]);             // cg.cc:110
+                        rs[cc][e] = __fma_rn(-alpha, apv[cc * EPT + e], rs[cc][e]);    // cg.cc:113
+                        sq[cc][e] = __dmul_rn(rs[cc][e], rs[cc][e]);                   // cg.cc:116
                     }
                 }
+            publish_chunk_partials(sq, rrview, tag, a.rrpart);
+        }
+        if (rec) rec[2] = globaltimer_ns();
+
+        // ---- re-balancing (off the critical path: the r'r partials of the other CTAs are still on
+        // their way): rows for mat-vec m + 2 in proportion to the speed every CTA showed in this one.
+        // Every CTA computes the same boundaries from the same 148 numbers; no result bit depends on them.
+        if (balance && warp == CW - 1) {
+            const int par = m & 1;
+            if (rebalance_now) {
+                // this parity's slot still holds the partition of mat-vec m: the producer must have
+                // taken it (it normally did an iteration ago; a CTA without rows can run ahead of it)
+                if (lane == 0) {
+                    const unsigned long long t0 = globaltimer_ns();
+                    while (s_prod_geo < m) {
+                        __nanosleep(64);
+                        if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 6);
+                    }
+                }
+                __syncwarp();
+                constexpr int PER = kMaxGrid / 32;
+                const uint4 *src[PER];
+                double tmv[PER];
+                unsigned pending = 0;
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    src[u] = tmview + lane * PER + u;
+                    if (lane * PER + u < nblk) pending |= 1u << u;
+                }
+                ll_wait_batch<PER>(a, src, pending, tag, tmv);
+                // speed of CTA k = rows / time; CTAs without rows (or a zero reading) get the mean speed
+                double sp[PER], ssum = 0.0;
+                int nz = 0;
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int k = lane * PER + u;
+                    sp[u] = 0.0;
+                    if (k < nblk) {
+                        const int rk = s_bnd[par][k + 1] - s_bnd[par][k];
+                        if (rk > 0 && tmv[u] > 0.0) {
+                            sp[u] = (double)rk / tmv[u];
+                            ssum += sp[u];
+                            ++nz;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    ssum += __shfl_xor_sync(0xffffffffu, ssum, off);
+                    nz += __shfl_xor_sync(0xffffffffu, nz, off);
+                }
+                const double mean = nz > 0 ? ssum / nz : 1.0;
+                double lsum = 0.0;
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    if (lane * PER + u < nblk && sp[u] == 0.0) sp[u] = mean;
+                    if (lane * PER + u < nblk) lsum += sp[u];
+                }
+                // exclusive prefix of the speeds over the CTAs (lane-major), total in every lane
+                double incl = lsum;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const double up = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += up;
+                }
+                const double total = __shfl_sync(0xffffffffu, incl, 31);
+                double run = incl - lsum;
+                int nbv[PER];
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int k = lane * PER + u;
+                    nbv[u] = 0;
+                    if (k < nblk) {
+                        // boundary k of the speed-proportional split, blended 1:1 with the current one:
+                        // floor of a sum of two non-decreasing sequences -- stays non-decreasing
+                        const double target = (double)a.rows * (run / total);
+                        nbv[u] = (int)(0.5 * (target + (double)s_bnd[par][k]) + 0.5);
+                        if (nbv[u] > (int)a.rows) nbv[u] = (int)a.rows;
+                        run += sp[u];
+                    }
+                }
+                __syncwarp(); // all reads of the old boundaries are done
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int k = lane * PER + u;
+                    if (k > 0 && k < nblk) s_bnd[par][k] = nbv[u]; // ends stay 0 and rows
+                }
             }
-            if (rec) rec[2] = globaltimer_ns();
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                s_part_seq = m + 2; // partition of mat-vec m + 2 = this parity's slot, updated or not
+            }
         }
 
         // ------------------------------------------------ phase B: r'r, stop test, beta (cg.cc:116-124)
-        {
-            constexpr int PB = 3;
-            for (unsigned t0 = tid; t0 < nchunks; t0 += PB * NCT) {
-                const uint4 *src[PB];
-                double val[PB];
-                unsigned pending = 0;
-#pragma unroll
-                for (int u = 0; u < PB; ++u) {
-                    src[u] = rrview + t0 + u * NCT;
-                    if (t0 + u * NCT < nchunks) pending |= 1u << u;
-                }
-                ll_wait_batch<PB>(a, src, pending, tag, val);
-#pragma unroll
-                for (int u = 0; u < PB; ++u)
-                    if (t0 + u * NCT < nchunks) scr[t0 + u * NCT] = val[u];
-            }
-        }
-        named_bar_sync(1, NCT);
-        if (warp == 0) {
-            const double s = warp_det_sum_smem(scr, (int)nchunks, lane);
-            if (lane == 0) s_sc[2] = s;
-        }
-        named_bar_sync(1, NCT);
-        rsnew = s_sc[2];
+        rsnew = collect_chunk_partials(rrview, tag, 2);
         executed = m + 1;
         if (rec) rec[4] = globaltimer_ns();
         if (c == 0 && tid == 0 && a.hist) a.hist[jloop] = rsnew;
@@ -632,6 +766,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
             rec[6] = globaltimer_ns();
         }
     }
+    if (tid == 0) s_stop = 1; // the producer may be waiting for a partition that will never come
 
     // ---- hand the state back: x, r of the own chunks (p is already in place), scalars by CTA 0
 #pragma unroll
@@ -673,7 +808,7 @@ template <int CW, int RPW, int TC, int STAGES>
 size_t persist_smem(const PersistArgs &a)
 {
     return (size_t)STAGES * CW * RPW * TC * 8 + (size_t)STAGES * persist_pmax(CW * RPW * TC, TC) * 8 + 2 * STAGES * 8 +
-           (kPersistMaxChunks * 8 + 4) * 8 + ((size_t)a.qs_n + (size_t)a.scr_n) * 8;
+           (kPersistMaxChunks * 8 + 4) * 8 + (size_t)a.scr_n * 8;
 }
 
 template <int CW, int RPW, int TC, int STAGES>

@@ -7,7 +7,8 @@
 // gather of the mat-vec result (see capi.cu).
 //
 // Reduction order (mirrored by oracle/cg_oracle.c): 256-element chunk partials (perfect xor
-// tree) -> det_sum over the chunk partials; p'Ap = det_sum over the mat-vec block partials.
+// tree) of the GLOBAL vector -> det_sum over the chunk partials, for p'Ap and r'r alike.  Nothing
+// depends on which CTA / SM / GPU computed a row of Ap.
 #include "cgb_device.cuh"
 #include "cgb_kernels.h"
 
@@ -48,9 +49,27 @@ __global__ void __launch_bounds__(kChunk) init_residual_kernel(const VecArgs a)
     exchange_consumed(a.g, tid);
 }
 
-__global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a)
+// chunk partials of p'Ap from the gathered rows (cg.cc:105): level 1 of the two-level reduction
+__global__ void __launch_bounds__(kChunk) pap_partials_kernel(const VecArgs a)
 {
-    extern __shared__ double sh_part[]; // world * nblk block partials
+    __shared__ double wsum[8];
+    const int tid = threadIdx.x;
+    griddep_launch_dependents(); // let update_xr become resident
+    griddep_wait();              // ... but read nothing before the mat-vec has completed
+    if (a.st->done) return;
+    // fused exchange: every read polls its own LL entry until the owning rank's mat-vec has
+    // delivered it over NVLink -- this kernel may start while peers are still streaming A
+    const GatherView gv = gather_view(a.apx, a.g);
+    const long long i = (long long)blockIdx.x * kChunk + tid;
+    const double v = (i < a.n) ? __dmul_rn(a.p[i], gather_read(gv, gather_index(a.g, i))) : 0.0;
+    const double t = block_chunk256(v, wsum, tid);
+    if (tid == 0) a.papart[blockIdx.x] = t;
+    // the exchange stays open: update_xr reads the same rows again and closes it
+}
+
+__global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a, long long nchunks)
+{
+    extern __shared__ double sh_part[]; // nchunks chunk partials of p'Ap
     __shared__ double wsum[8];
     __shared__ double sh_alpha;
     const int tid = threadIdx.x;
@@ -61,20 +80,14 @@ __global__ void __launch_bounds__(kChunk) update_xr_kernel(const VecArgs a)
         trace_stamp(rec, 0);
     }
     griddep_launch_dependents(); // let update_p (and, behind it, the next mat-vec) become resident
-    griddep_wait();              // ... but read nothing before the mat-vec has completed
+    griddep_wait();              // pap_partials has completed
     trace_stamp(rec, 1);
     if (a.st->done) return;
-    // fused exchange: every read below polls its own LL entry until the owning rank's mat-vec
-    // has delivered it over NVLink -- this kernel may start while peers are still streaming A
     const GatherView gv = gather_view(a.apx, a.g);
-    const int total = a.g.world * a.g.nblk;
-    for (int t = tid; t < total; t += kChunk) {
-        const int r = t / a.g.nblk, c = t - r * a.g.nblk;
-        sh_part[t] = gather_read(gv, (long long)r * a.g.slot + a.g.maxrows + c);
-    }
+    for (long long t = tid; t < nchunks; t += kChunk) sh_part[t] = a.papart[t];
     __syncthreads();
     if (tid < 32) {
-        const double conj = warp_det_sum(sh_part, total, tid);        // p'Ap     cg.cc:105-106
+        const double conj = warp_det_sum(sh_part, nchunks, tid);      // p'Ap     cg.cc:105-106
         const double rsold = a.st->rsold;
         const double clamp = __dmul_rn(rsold, kNearZero);
         const double alpha = __ddiv_rn(rsold, (conj < clamp) ? clamp : conj); // cg.cc:107
@@ -211,10 +224,16 @@ __global__ void __launch_bounds__(32) sum_kernel(const double *v, long long n, d
     if (threadIdx.x == 0) out[0] = s;
 }
 
-__global__ void __launch_bounds__(32) sum_partials_kernel(const double *apx, const Gather g, double *out)
+// hooks: chunk partials of v.(A v) from the PLAIN gather buffer (after exchange_collect)
+__global__ void __launch_bounds__(kChunk) pap_plain_kernel(const double *v, const double *apx, const Gather g,
+                                                            long long n, double *papart)
 {
-    const double s = warp_det_sum_partials(apx, g, threadIdx.x);
-    if (threadIdx.x == 0) out[0] = s;
+    __shared__ double wsum[8];
+    const int tid = threadIdx.x;
+    const long long i = (long long)blockIdx.x * kChunk + tid;
+    const double q = (i < n) ? __dmul_rn(v[i], apx[gather_index(g, i)]) : 0.0;
+    const double t = block_chunk256(q, wsum, tid);
+    if (tid == 0) papart[blockIdx.x] = t;
 }
 
 // Fused mode, test hooks only: consume the running exchange into the plain buffer (every rank's
@@ -223,13 +242,13 @@ __global__ void __launch_bounds__(kChunk) exchange_collect_kernel(double *apx, c
 {
     const int tid = threadIdx.x;
     const GatherView gv = gather_view(apx, g);
-    const long long per = g.maxrows + g.nblk;
+    const long long per = g.maxrows;
     const long long total = (long long)g.world * per;
     for (long long t = (long long)blockIdx.x * kChunk + tid; t < total; t += (long long)gridDim.x * kChunk) {
         const int r = (int)(t / per);
         const long long e = t - (long long)r * per;
         const long long rows_r = (r == g.world - 1) ? g.maxrows : g.n_loc;
-        if (e < rows_r || e >= g.maxrows) {
+        if (e < rows_r) {
             const long long idx = (long long)r * g.slot + e;
             apx[idx] = gather_read(gv, idx);
         }
@@ -290,6 +309,7 @@ cudaError_t preload_vec_kernels()
     cudaFuncAttributes fa;
     cudaError_t e;
     if ((e = cudaFuncGetAttributes(&fa, init_residual_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&fa, pap_partials_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&fa, update_xr_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&fa, update_p_kernel)) != cudaSuccess) return e;
     if ((e = cudaFuncGetAttributes(&fa, finalize_kernel)) != cudaSuccess) return e;
@@ -304,10 +324,16 @@ cudaError_t launch_init_residual(const VecArgs &a, cudaStream_t s)
     return cudaGetLastError();
 }
 
+cudaError_t launch_pap_partials(const VecArgs &a, cudaStream_t s)
+{
+    return launch_kernel(pap_partials_kernel, grid_for(a.n), kChunk, 0, s, a.pdl != 0, a);
+}
+
 cudaError_t launch_update_xr(const VecArgs &a, cudaStream_t s)
 {
-    const size_t smem = (size_t)a.g.world * a.g.nblk * sizeof(double);
-    return launch_kernel(update_xr_kernel, grid_for(a.n), kChunk, smem, s, a.pdl != 0, a);
+    const long long nchunks = grid_for(a.n);
+    return launch_kernel(update_xr_kernel, (int)nchunks, kChunk, (size_t)nchunks * sizeof(double), s, a.pdl != 0,
+                         a, nchunks);
 }
 
 cudaError_t launch_update_p(const VecArgs &a, cudaStream_t s)
@@ -340,15 +366,18 @@ cudaError_t launch_dot(const double *a, const double *b, long long n, double *sc
     return cudaGetLastError();
 }
 
-cudaError_t launch_sum_partials(const double *apx, const Gather &g, double *out, cudaStream_t s)
+cudaError_t launch_pap_plain(const double *v, const double *apx, const Gather &g, long long n, double *papart,
+                             double *out, cudaStream_t s)
 {
-    sum_partials_kernel<<<1, 32, 0, s>>>(apx, g, out);
+    const long long nchunks = grid_for(n);
+    pap_plain_kernel<<<(int)nchunks, kChunk, 0, s>>>(v, apx, g, n, papart);
+    sum_kernel<<<1, 32, 0, s>>>(papart, nchunks, out);
     return cudaGetLastError();
 }
 
 cudaError_t launch_exchange_collect(double *apx, const Gather &g, cudaStream_t s)
 {
-    const long long total = (long long)g.world * (g.maxrows + g.nblk);
+    const long long total = (long long)g.world * g.maxrows;
     long long blocks = (total + kChunk - 1) / kChunk;
     if (blocks > 296) blocks = 296;
     exchange_collect_kernel<<<(int)blocks, kChunk, 0, s>>>(apx, g);

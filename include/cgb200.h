@@ -151,7 +151,7 @@ int cgb_autotune(cgb_ctx *ctx, int iters, int *chosen, float *us_per_iter);
 typedef struct cgb_layout {
     int64_t n, ld, rows, row0; /* shard geometry */
     int rank, world, device;
-    int nblk;                  /* mat-vec grid = number of p'Ap block partials per rank */
+    int nblk;                  /* mat-vec grid (CTAs); no reduction depends on it */
     int sm_count;
     int64_t nchunks;           /* 256-element chunks of the r'r reduction */
 } cgb_layout;
@@ -190,9 +190,11 @@ int cgb_residual_check(cgb_ctx *ctx, double *norm_x, double *rel_resid);
 
 /* ---- kernel-level hooks (tests, ncu, roofline) ------------------------------------------ */
 /* y = A_shard . v through the production mat-vec: v_host has n doubles; y_host (nullable)
- * receives this rank's `rows` results, block_partials (nullable) the nblk partial sums of
- * v_i * y_i, pAp (nullable) their deterministic total over all ranks. */
-int cgb_gemv(cgb_ctx *ctx, const double *v_host, double *y_host, double *block_partials,
+ * receives this rank's `rows` results, chunk_partials (nullable, `nchunks` of cgb_get_layout) the
+ * partial sums of v_i * (A v)_i over the 256-element chunks of the GLOBAL vector (all ranks'
+ * rows, after the exchange), pAp (nullable) their deterministic total -- level 1 and 2 of the
+ * reduction that replaces cblas_ddot + MPI_Allreduce (cg.cc:105-106). */
+int cgb_gemv(cgb_ctx *ctx, const double *v_host, double *y_host, double *chunk_partials,
              double *pAp);
 /* Deterministic two-level dot of two host vectors (n doubles each) on the device. */
 int cgb_dot(cgb_ctx *ctx, const double *a_host, const double *b_host, double *result);

@@ -157,22 +157,6 @@ double cgo_dot(const double *a, const double *b, int64_t n)
     return s;
 }
 
-/* p'Ap over the emulated ranks: block partials in (rank, block) order */
-static double pAp_blocks(int64_t n, const double *p, const double *Ap, int nranks, int nblk,
-                         const int64_t *start, const int64_t *num, double *bp, double *q)
-{
-    (void)n;
-    for (int r = 0; r < nranks; ++r) {
-        for (int c = 0; c < nblk; ++c) {
-            int64_t r0, r1;
-            cgo_block_range(num[r], nblk, c, &r0, &r1);
-            for (int64_t i = r0; i < r1; ++i) q[i - r0] = p[start[r] + i] * Ap[start[r] + i];
-            bp[r * nblk + c] = cgo_det_sum(q, r1 - r0);
-        }
-    }
-    return cgo_det_sum(bp, (int64_t)nranks * nblk);
-}
-
 /* ------------------------------------------------------------------- solve */
 
 void cgo_residual_check(int64_t n, const double *A, int64_t ld, const double *b,
@@ -191,15 +175,15 @@ void cgo_solve(int64_t n, const double *A, int64_t ld, const double *b, double *
                int64_t max_iter, double tol, int nranks, int nblk,
                double *hist, cgo_info *info)
 {
-    int64_t *start = (int64_t *)malloc(sizeof(int64_t) * (size_t)nranks);
-    int64_t *num = (int64_t *)malloc(sizeof(int64_t) * (size_t)nranks);
-    cgo_partition(n, nranks, start, num); /* cg.cc:60-68 */
+    /* cg.cc:60-68 shards the rows over the ranks; every reduction below is defined on the GLOBAL
+     * vectors (row results do not depend on who computes them), so neither the rank count nor
+     * the mat-vec grid enters the arithmetic -- the parameters are kept for the callers. */
+    (void)nranks;
+    (void)nblk;
 
     double *r = (double *)malloc(sizeof(double) * (size_t)n);
     double *p = (double *)malloc(sizeof(double) * (size_t)n);
     double *Ap = (double *)malloc(sizeof(double) * (size_t)n);
-    double *bp = (double *)malloc(sizeof(double) * (size_t)nranks * (size_t)nblk);
-    double *q = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
 
     /* cg.cc:77-82: r = b - A x  (row results do not depend on the sharding) */
     cgo_gemv(n, n, A, ld, x, Ap);
@@ -214,7 +198,7 @@ void cgo_solve(int64_t n, const double *A, int64_t ld, const double *b, double *
     int64_t k = 0;
     for (; k < max_iter; ++k) { /* cg.cc:96 */
         cgo_gemv(n, n, A, ld, p, Ap);                                  /* :100-102 */
-        double conj = pAp_blocks(n, p, Ap, nranks, nblk, start, num, bp, q); /* :105-106 */
+        double conj = cgo_dot(p, Ap, n);                               /* :105-106 */
         double clamp = rsold * NEARZERO;
         double alpha = rsold / ((conj < clamp) ? clamp : conj);        /* :107 std::max */
         for (int64_t i = 0; i < n; ++i) x[i] = fma(alpha, p[i], x[i]); /* :110 */
@@ -235,5 +219,5 @@ void cgo_solve(int64_t n, const double *A, int64_t ld, const double *b, double *
         info->rsnew = rsnew;
         cgo_residual_check(n, A, ld, b, x, &info->norm_x, &info->rel_resid);
     }
-    free(start); free(num); free(r); free(p); free(Ap); free(bp); free(q);
+    free(r); free(p); free(Ap);
 }

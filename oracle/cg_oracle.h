@@ -27,11 +27,11 @@
  *       starting from +0.0), then the same butterfly.
  *   chunk256(v): perfect xor tree over 256 consecutive elements
  *       (offsets 16,8,4,2,1 inside each 32-group, then 128,64,32 across groups).
- *   p'Ap  = det_sum over (rank-major, block-minor) block partials, block
- *       partial = det_sum(p_i * Ap_i over the block's contiguous rows); the
- *       blocks of a rank are the balanced contiguous split of its rows into
- *       `nblk` ranges (the GEMV grid size).
- *   r'r   = det_sum over chunk256 partials of r_i * r_i over the GLOBAL vector.
+ *   p'Ap  = det_sum over chunk256 partials of p_i * Ap_i over the GLOBAL vector,
+ *   r'r   = det_sum over chunk256 partials of r_i * r_i over the GLOBAL vector
+ *       (the same two-level tree for both): no reduction depends on how rows are
+ *       distributed over GPUs, CTAs or ranks, so 1, 2, 4 and 8 GPUs -- and any
+ *       dynamic re-balancing of rows between SMs -- give the same bits.
  *   x_i = fma(alpha, p_i, x_i); r_i = fma(-alpha, Ap_i, r_i); p_i = fma(beta, p_i, r_i).
  *
  * Parity pin: validated here against the reference's own sources compiled
@@ -85,8 +85,8 @@ typedef struct {
     double  rel_resid;    /* DEBUG block: ||Ax-b|| / ||b|| */
 } cgo_info;
 
-/* cg.cc:38-156 restated with `nranks` emulated ranks (row shards by
- * cgo_partition) and `nblk` GEMV blocks per rank.  A: n*n, ld.  x: in = x0,
+/* cg.cc:38-156 restated.  `nranks` / `nblk` (emulated ranks, mat-vec grid) no longer enter the
+ * arithmetic -- see the reduction order above; kept in the signature.  A: n*n, ld.  x: in = x0,
  * out = solution.  hist (nullable): rsnew of every executed iteration
  * (hist[j] = rsnew computed in loop index j), capacity max_iter. */
 void cgo_solve(int64_t n, const double *A, int64_t ld, const double *b, double *x,

@@ -92,6 +92,17 @@ def partition(n: int, psize: int):
     return list(s), list(c)
 
 
+def chunk_partials(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Level 1 of the two-level dot: the chunk256 partials of a_i * b_i over 256-element chunks."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    n = a.size
+    out = np.empty((n + 255) // 256, dtype=np.float64)
+    for c in range(out.size):       # a chunk alone IS a one-chunk dot: det_sum of one value = the value
+        out[c] = dot(a[256 * c:256 * (c + 1)], b[256 * c:256 * (c + 1)])
+    return out
+
+
 def block_range(rows: int, nblk: int, c: int):
     r0, r1 = C.c_int64(), C.c_int64()
     lib().cgo_block_range(rows, nblk, c, C.byref(r0), C.byref(r1))

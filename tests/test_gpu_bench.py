@@ -54,8 +54,8 @@ def test_bench_line_graph_schedule():
     """--schedule 0: the three-kernel CUDA graph; the roofline kernel is then the mat-vec."""
     d = _bench("--size", "4096", "--iters", "50", "--steps", "3", "--warmup", "3", "--no-cpu-baseline",
                "--schedule", "0")
-    # 3 launches per iteration (mat-vec, update_xr, update_p) + init (2) + finalize (1) per step
-    assert d["gpu_launches"] == 3 * (3 * 50 + 3) and "graph" in d["config"]["schedule"]
+    # 4 launches per iteration (mat-vec, p'Ap partials, update_xr, update_p) + init (2) + finalize (1) per step
+    assert d["gpu_launches"] == 3 * (4 * 50 + 3) and "graph" in d["config"]["schedule"]
     rf = d["roofline"]
     assert rf["algorithmic_bytes_per_launch"] == 8.0 * 4096 * 4096 and rf["launches_timed"] == 50
 

@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from parity_util import check_against_reference
+from parity_util import check_against_reference, reference_k_set
 
 pytestmark = pytest.mark.gpu
 
@@ -81,13 +81,11 @@ def test_gemv_every_variant_bitwise(cgb, O, n):
         ctx.set_matrix_rows(A)
         for v, name in enumerate(cgb.gemv_variants()):
             ctx.set_option("gemv_variant", v)
-            nblk = ctx.layout().nblk
-            y, bp, pap = ctx.gemv(p, want_partials=True)
+            y, cp, pap = ctx.gemv(p, want_partials=True)
             assert np.array_equal(y, y_ref), name
-            bp_ref = np.array([O.det_sum((p * y_ref)[slice(*O.block_range(n, nblk, c))])
-                               for c in range(nblk)])
-            assert np.array_equal(bp, bp_ref), name
-            assert pap == O.det_sum(bp_ref), name
+            cp_ref = O.chunk_partials(p, y_ref)     # chunk256 partials of p_i * (A p)_i, global vector
+            assert np.array_equal(cp, cp_ref), name
+            assert pap == O.det_sum(cp_ref) == O.dot(p, y_ref), name
 
 
 def test_gemv_exactness_properties(cgb, O):
@@ -160,8 +158,8 @@ def test_solve_generated_bitwise_vs_oracle(cgb, O, n, max_iter, sched):
 
 
 def test_solve_nonzero_x0_and_variants(cgb, O):
-    """x0 != 0 exercises the init mat-vec (cg.cc:77-82); all variants give the same bits
-    when their grids (nblk) agree, and the oracle's bits for their own nblk otherwise."""
+    """x0 != 0 exercises the init mat-vec (cg.cc:77-82); every variant -- whatever its grid and tile
+    shape -- gives the oracle's bits (no reduction depends on how rows are spread over CTAs)."""
     n = 1536
     rng = _rng(3)
     A = O.generate_lap2d(n)
@@ -302,7 +300,10 @@ def test_solve_matches_reference_golden(cgb, O, golden_dir, tmp_path):
                 ctx.generate_lap2d()
                 ctx.set_rhs(b)
         x, info, hist, nx, rr, _ = _solve_gpu(cgb, n, setup, max_iter)
-        check_against_reference(info.k, hist, x, g, "openblas", os.path.basename(f))
+        # k within +-1 of a count the reference itself produces for this system (its BLAS providers
+        # disagree in the rounding-noise tail: N = 4096 stops at 358 with OpenBLAS, 385 with plain loops)
+        check_against_reference(info.k, hist, x, g, "openblas", os.path.basename(f),
+                                k_refs=reference_k_set(golden_dir, g))
         assert abs(nx - float(g["openblas_norm_x"])) <= 1e-6 * nx
 
 
@@ -361,11 +362,10 @@ def test_compat_topologies_bitwise_vs_oracle(cgb, O, nt, bw):
             ctx.set_option("block_width", bw)
             ctx.set_option("transposed", transposed)
             ctx.set_option("compat", 1)
-            assert ctx.layout().nblk == 148
-            y, bp, pap = ctx.gemv(p, want_partials=True)
+            y, cp, pap = ctx.gemv(p, want_partials=True)
             assert np.array_equal(y, y_ref), (transposed, nt, bw)
-            bp_ref = np.array([O.det_sum((p * y_ref)[slice(*O.block_range(n, 148, c))]) for c in range(148)])
-            assert np.array_equal(bp, bp_ref) and pap == O.det_sum(bp_ref)
+            cp_ref = O.chunk_partials(p, y_ref)
+            assert np.array_equal(cp, cp_ref) and pap == O.det_sum(cp_ref)
             x = np.zeros(n)
             info, hist = ctx.solve(x, max_iter=60, tol=1e-10, history=True)
             assert info.k == ref.k and np.array_equal(hist, ref.hist) and np.array_equal(x, ref.x)

@@ -39,7 +39,11 @@ def test_oracle_matches_reference_golden(O, golden_dir, tmp_path):
                                     k_refs=reference_k_set(golden_dir, g))
             continue
         r = O.solve(A, b, max_iter=int(g["max_iter"]), nranks=1, nblk=148)
-        check_against_reference(r.k, r.hist, r.x, g, "openblas", os.path.basename(f))
+        # the count may land on any value the reference itself shows for this system over its BLAS
+        # providers and rank counts (N = 4096: 358 with OpenBLAS, 385 with plain loops): the stopping
+        # rule sits below fp64's attainable accuracy, the tail is summation-order noise
+        check_against_reference(r.k, r.hist, r.x, g, "openblas", os.path.basename(f),
+                                k_refs=reference_k_set(golden_dir, g))
         assert abs(r.norm_x - float(g["openblas_norm_x"])) <= 1e-6 * r.norm_x
         line = O.debug_line(r.k, r.rsold, r.norm_x, r.rel_resid)
         assert line.split("residual")[0] == "\t[STEP %d] " % r.k
@@ -131,18 +135,14 @@ def test_reductions_are_the_specified_trees(O):
 
 
 def test_emulated_ranks_agree_with_one_rank(O):
-    """Row results do not depend on the sharding; only the p'Ap block order does, so P-rank
-    runs track the 1-rank run to rounding for the pre-floor segment and give the same x."""
+    """Row results do not depend on the sharding, and every reduction is defined on the global
+    vectors: a P-rank run (any mat-vec grid) is the 1-rank run, bit for bit."""
     n = 1024
     A, b = O.generate_lap2d(n), O.init_source_term(n)
     r1 = O.solve(A, b, nranks=1, nblk=148)
-    for P in (2, 3, 8):
-        rp = O.solve(A, b, nranks=P, nblk=148)
-        assert abs(rp.k - r1.k) <= 1
-        m = min(prefloor_length(r1.hist), len(rp.hist))
-        rel = np.abs(np.sqrt(rp.hist[:m]) - np.sqrt(r1.hist[:m])) / np.sqrt(r1.hist[:m])
-        assert rel.max() <= 1e-10
-        assert np.linalg.norm(rp.x - r1.x) <= 1e-9 * np.linalg.norm(r1.x)
+    for P, nblk in ((2, 148), (3, 296), (8, 7)):
+        rp = O.solve(A, b, nranks=P, nblk=nblk)
+        assert rp.k == r1.k and np.array_equal(rp.hist, r1.hist) and np.array_equal(rp.x, r1.x)
 
 
 def test_mtx_reader_restatement(O, tmp_path):
