@@ -117,6 +117,8 @@ struct cgb_ctx {
     double *compat_part = nullptr; // chunk partials of the compat mat-vec
     size_t compat_part_cap = 0;
     int poll_every = 16, graph_unroll = 16, opt_pdl = 1, opt_l2_prefetch = 4;
+    int graph_len = 0;             // iterations in the instantiated graph (min(graph_unroll, poll_every))
+    long long graph_replays = 0;   // graph launches since creation ("graph_replays", read-only option)
     int opt_balance = 1;           // persistent kernel: re-balance the rows between the CTAs from measured speeds
     long long aux_stride = 0;      // entries of one parity of the local LL side buffer
     int opt_schedule = 1;          // 1: persistent cooperative kernel (persist.cu) when usable, 0: graph of 3 kernels
@@ -185,6 +187,8 @@ Gather make_gather(const cgb_ctx *c)
     g.ll = c->ll;
     g.ctl = c->ctl;
     g.p2p = (c->world > 1 && c->opt_exchange == 1) ? 1 : 0;
+    g.spin_ns = (unsigned long long)c->spin_timeout_ms * 1000000ULL;
+    g.host_err = c->d_hdone;
     return g;
 }
 
@@ -328,7 +332,9 @@ int build_graph(cgb_ctx *c)
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int rc = CGB_OK;
     const long long before = c->kernel_launches;
-    for (int u = 0; u < c->graph_unroll && rc == CGB_OK; ++u) rc = launch_iteration(c);
+    // a batch between two looks at the stop flag is poll_every iterations: a longer graph could never be replayed
+    c->graph_len = c->graph_unroll < c->poll_every ? c->graph_unroll : c->poll_every;
+    for (int u = 0; u < c->graph_len && rc == CGB_OK; ++u) rc = launch_iteration(c);
     c->kernel_launches = before; // capture launches nothing
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
@@ -501,8 +507,8 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10)
-        return fail(CGB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+    if (prop.major != 10 || prop.minor != 0) // sm_100a SASS only: arch-specific, no forward-compatible PTX
+        return fail(CGB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
                     device, prop.major, prop.minor);
 
     cgb_ctx *c = new (std::nothrow) cgb_ctx;
@@ -764,48 +770,46 @@ extern "C" int cgb_set_matrix_coo(cgb_ctx *c, int64_t nz, const int32_t *irn, co
     if (rc) return rc;
     if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
     if (nz < 0 || (nz > 0 && (!irn || !jcn || !val))) return fail(CGB_ERR_INVALID, "bad COO arguments");
-    // Sequential "later entries overwrite" semantics (matrix.cc:12-21) under a parallel
-    // scatter: keep, for every destination cell, only the LAST entry that writes it.
-    std::unordered_map<long long, long long> last; // cell -> index of the last writer
-    last.reserve((size_t)nz * (symmetric ? 2 : 1));
-    for (long long z = 0; z < nz; ++z) {
-        const long long i = irn[z], j = jcn[z];
-        if (i < 0 || j < 0 || i >= c->n || j >= c->n)
-            return fail(CGB_ERR_INVALID, "COO entry %lld (%lld,%lld) outside %lld x %lld", z, i, j,
-                        c->n, c->n);
-        last[i * c->n + j] = z;
-        if (symmetric) last[j * c->n + i] = z;
-    }
-    // expand into plain (i, j, v) writes, at most one per cell
-    std::vector<int> ei, ej;
-    std::vector<double> ev;
-    ei.reserve(last.size());
-    ej.reserve(last.size());
-    ev.reserve(last.size());
-    for (const auto &kv : last) {
-        const long long i = kv.first / c->n, j = kv.first % c->n;
-        if (i < c->row0 || i >= c->row0 + c->rows) continue;
-        ei.push_back((int)i);
-        ej.push_back((int)j);
-        ev.push_back(val[kv.second]);
-    }
-    const long long m = (long long)ei.size();
+    // Sequential "later entries overwrite" semantics (matrix.cc:12-21) under a parallel scatter,
+    // resolved ON THE DEVICE: (1) every entry raises the cells it writes (inside this shard) to its
+    // own index + 1 with atomicMax, the shard's 8-byte cells serving as the index array; (2) an
+    // entry whose index survived in a cell is that cell's last writer; (3) the winners store
+    // their values.  Untouched cells keep the zero bits of step 0.  The host only copies the triples.
+    struct Tmp { // freed on every path
+        int *i = nullptr, *j = nullptr;
+        double *v = nullptr;
+        unsigned char *win = nullptr;
+        int *bad = nullptr;
+        ~Tmp()
+        {
+            cudaFree(i);
+            cudaFree(j);
+            cudaFree(v);
+            cudaFree(win);
+            cudaFree(bad);
+        }
+    } t;
     CK(cudaMemsetAsync(c->A, 0, (size_t)c->rows * c->ld * sizeof(double), c->stream));
-    if (m > 0) {
-        int *di = nullptr, *dj = nullptr;
-        double *dv = nullptr;
-        CK(cudaMalloc(&di, m * sizeof(int)));
-        CK(cudaMalloc(&dj, m * sizeof(int)));
-        CK(cudaMalloc(&dv, m * sizeof(double)));
-        CK(cudaMemcpyAsync(di, ei.data(), m * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(dj, ej.data(), m * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        CK(cudaMemcpyAsync(dv, ev.data(), m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        CK(launch_scatter_coo(c->A, c->ld, c->row0, c->rows, di, dj, dv, m, 0, c->stream));
-        c->kernel_launches += 1;
+    if (nz > 0) {
+        CK(cudaMalloc(&t.i, (size_t)nz * sizeof(int)));
+        CK(cudaMalloc(&t.j, (size_t)nz * sizeof(int)));
+        CK(cudaMalloc(&t.v, (size_t)nz * sizeof(double)));
+        CK(cudaMalloc(&t.win, (size_t)nz));
+        CK(cudaMalloc(&t.bad, sizeof(int)));
+        CK(cudaMemsetAsync(t.bad, 0, sizeof(int), c->stream));
+        CK(cudaMemcpyAsync(t.i, irn, (size_t)nz * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(t.j, jcn, (size_t)nz * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(t.v, val, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CK(launch_scatter_coo(c->A, c->n, c->ld, c->row0, c->rows, t.i, t.j, t.v, nz, symmetric ? 1 : 0, t.win,
+                              t.bad, c->stream));
+        c->kernel_launches += 3;
+        int bad = 0;
+        CK(cudaMemcpyAsync(&bad, t.bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        cudaFree(di);
-        cudaFree(dj);
-        cudaFree(dv);
+        if (bad) {
+            c->matrix_set = false;
+            return fail(CGB_ERR_INVALID, "a COO entry lies outside %lld x %lld", (long long)c->n, (long long)c->n);
+        }
     } else {
         CK(cudaStreamSynchronize(c->stream));
     }
@@ -990,6 +994,7 @@ extern "C" int cgb_get_option(cgb_ctx *c, const char *key, int64_t *value)
     else if (k == "profile") *value = c->opt_profile;
     else if (k == "poll_every") *value = c->poll_every;
     else if (k == "graph_unroll") *value = c->graph_unroll;
+    else if (k == "graph_replays") *value = c->graph_replays;
     else if (k == "compat") *value = c->opt_compat;
     else if (k == "pdl") *value = c->opt_pdl;
     else if (k == "l2_prefetch") *value = c->opt_l2_prefetch;
@@ -1113,7 +1118,9 @@ extern "C" int cgb_iterate(cgb_ctx *c, int64_t iters, float *ms)
         if (ms) *ms = t;
         return CGB_OK;
     }
-    if (graph && !c->graph_exec && todo >= c->graph_unroll) {
+    const int want_len = c->graph_unroll < c->poll_every ? c->graph_unroll : c->poll_every;
+    if (graph && c->graph_exec && c->graph_len != want_len) drop_graph(c);
+    if (graph && !c->graph_exec && todo >= want_len) {
         if ((rc = build_graph(c))) return rc;
     }
     if (profile) {
@@ -1131,10 +1138,11 @@ extern "C" int cgb_iterate(cgb_ctx *c, int64_t iters, float *ms)
         const long long batch = std::min<long long>(c->poll_every, todo - issued);
         long long i = 0;
         while (i < batch) {
-            if (graph && c->graph_exec && batch - i >= c->graph_unroll) {
+            if (graph && c->graph_exec && batch - i >= c->graph_len) {
                 CK(cudaGraphLaunch(c->graph_exec, c->stream));
-                c->kernel_launches += (c->opt_compat ? 5LL : 4LL) * c->graph_unroll;
-                i += c->graph_unroll;
+                c->kernel_launches += (c->opt_compat ? 5LL : 4LL) * c->graph_len;
+                c->graph_replays += 1;
+                i += c->graph_len;
             } else if (profile) {
                 const long long slot = 2 * (issued + i);
                 CK(cudaEventRecord(c->prof_ev[slot], c->stream));
@@ -1164,7 +1172,13 @@ extern "C" int cgb_iterate(cgb_ctx *c, int64_t iters, float *ms)
         ++batch_idx;
     }
     CK(cudaEventRecord(c->ev1, c->stream));
-    CK(cudaEventSynchronize(c->ev1));
+    {
+        cudaError_t e = cudaEventSynchronize(c->ev1);
+        if (e != cudaSuccess && *(volatile int *)c->h_done < 0)
+            return fail(CGB_ERR_TIMEOUT, "a wait for a peer rank's mat-vec rows exceeded spin_timeout_ms = %lld: "
+                        "a rank is missing or stuck (%s)", c->spin_timeout_ms, cudaGetErrorString(e));
+        CK(e);
+    }
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
     c->loop_ms += t;
@@ -1306,6 +1320,7 @@ extern "C" int cgb_bench_gemv(cgb_ctx *c, int variant, int reps, float *ms_avg)
     if (variant != keep_variant) {
         set_variant(c, variant);
         drop_graph(c);
+        CK(gemv_variant(variant).preload()); // loads the kernel and sets its shared-memory limit
     }
     CK(cudaMemsetAsync(&c->st->done, 0, sizeof(int), c->stream));
     if ((rc = launch_matvec(c, c->p, 0, variant))) return rc; // warm-up

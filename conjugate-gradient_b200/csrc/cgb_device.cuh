@@ -49,6 +49,8 @@ struct Gather {
     int world;
     int nblk;
     int p2p;           // 1: fused mode
+    unsigned long long spin_ns; // bound of a wait for a peer's entry (option "spin_timeout_ms")
+    int *host_err;     // mapped pinned flag: set to -1 before the launch is faulted on a timeout
 };
 
 // Diagnostic timeline (option "trace" = launches kept): every CTA of a traced kernel stamps
@@ -193,9 +195,10 @@ __device__ __forceinline__ void ll_store(uint4 *dst, double v, unsigned tag)
                  "r"(tag)
                  : "memory");
 }
-// consumer: poll the entry until both halves carry the tag.  Bounded: a dead peer faults the
-// launch (trap) instead of hanging the GPU.
-__device__ __forceinline__ double ll_load(const uint4 *src, unsigned tag)
+// consumer: poll the entry until both halves carry the tag.  Bounded (option "spin_timeout_ms"):
+// a dead or missing peer is reported through the mapped host flag, then the launch is faulted
+// (trap) instead of hanging the GPU -- the C ABI returns CGB_ERR_TIMEOUT.
+__device__ __forceinline__ double ll_load(const uint4 *src, unsigned tag, unsigned long long spin_ns, int *host_err)
 {
     unsigned lo, f0, hi, f1;
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src) : "memory");
@@ -203,7 +206,13 @@ __device__ __forceinline__ double ll_load(const uint4 *src, unsigned tag)
         const unsigned long long t0 = globaltimer_ns();
         do {
             asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(src) : "memory");
-            if (globaltimer_ns() - t0 > 20000000000ULL) __trap();
+            if (globaltimer_ns() - t0 > spin_ns) {
+                if (host_err) {
+                    *host_err = -1;
+                    __threadfence_system();
+                }
+                __trap();
+            }
         } while (f0 != tag || f1 != tag);
     }
     return __hiloint2double((int)hi, (int)lo);
@@ -218,6 +227,8 @@ struct GatherView {
     const uint4 *ll;
     unsigned tag;
     int p2p;
+    unsigned long long spin_ns;
+    int *host_err;
 };
 __device__ __forceinline__ GatherView gather_view(const double *apx, const Gather &g)
 {
@@ -226,11 +237,13 @@ __device__ __forceinline__ GatherView gather_view(const double *apx, const Gathe
     v.p2p = g.p2p;
     v.tag = g.p2p ? exchange_tag(g.ctl) : 0u;
     v.ll = g.ll + (long long)(v.tag & 1u) * g.bufstride;
+    v.spin_ns = g.spin_ns;
+    v.host_err = g.host_err;
     return v;
 }
 __device__ __forceinline__ double gather_read(const GatherView &v, long long idx)
 {
-    return v.p2p ? ll_load(v.ll + idx, v.tag) : v.plain[idx];
+    return v.p2p ? ll_load(v.ll + idx, v.tag, v.spin_ns, v.host_err) : v.plain[idx];
 }
 // Called by ALL threads of every block of a consumer kernel after its last gather_read: the
 // last block to finish advances the epoch, so the next mat-vec tags (and double-buffers) anew.

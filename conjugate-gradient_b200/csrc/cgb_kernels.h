@@ -106,9 +106,10 @@ cudaError_t launch_exchange_collect(double *apx, const Gather &g, cudaStream_t s
 // generate_lap2d_matrix (cg.cc:159-188) into the shard
 cudaError_t launch_generate_lap2d(double *A, long long n, long long ld, long long row0,
                                   long long rows, cudaStream_t s);
-// COO scatter, entries [z0, z1) -- sequential semantics are kept by the caller (see capi.cu)
-cudaError_t launch_scatter_coo(double *A, long long ld, long long row0, long long rows,
+// Matrix::read's densification (matrix.cc:12-21) on the device, "later entries overwrite" resolved
+// with an atomicMax of the entry index per cell (win: nz bytes of scratch, bad: 1 int, both device)
+cudaError_t launch_scatter_coo(double *A, long long n, long long ld, long long row0, long long rows,
                                const int *irn, const int *jcn, const double *val, long long nz,
-                               int symmetric, cudaStream_t s);
+                               int symmetric, unsigned char *win, int *bad, cudaStream_t s);
 
 } // namespace cgb

@@ -319,12 +319,9 @@ size_t tma_smem(long long rows_per_cta)
 template <int CW, int RPW, int TC, int STAGES, int MINB, int POL = 0>
 cudaError_t tma_launch(const GemvArgs &a, int nblk, cudaStream_t s)
 {
-    const long long rpc = (a.rows + nblk - 1) / nblk;
-    const size_t smem = tma_smem<CW, RPW, TC, STAGES>(rpc);
+    const size_t smem = tma_smem<CW, RPW, TC, STAGES>(0);
     auto k = gemv_tma_kernel<CW, RPW, TC, STAGES, MINB, POL>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return launch_kernel(k, nblk, (CW + 1) * 32, smem, s, a.pdl != 0, a);
+    return launch_kernel(k, nblk, (CW + 1) * 32, smem, s, a.pdl != 0, a); // smem attribute: set by the preload
 }
 
 // Lazy module loading would otherwise load the kernel at its first launch -- inside the caller's
@@ -333,7 +330,11 @@ template <int CW, int RPW, int TC, int STAGES, int MINB, int POL = 0>
 cudaError_t tma_preload()
 {
     cudaFuncAttributes fa;
-    return cudaFuncGetAttributes(&fa, gemv_tma_kernel<CW, RPW, TC, STAGES, MINB, POL>);
+    auto k = gemv_tma_kernel<CW, RPW, TC, STAGES, MINB, POL>;
+    cudaError_t e = cudaFuncGetAttributes(&fa, k);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)tma_smem<CW, RPW, TC, STAGES>(0));
 }
 template <int W, int RPW, int UNR>
 cudaError_t ldg_preload()

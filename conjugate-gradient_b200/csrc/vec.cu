@@ -287,17 +287,54 @@ __global__ void __launch_bounds__(256) generate_lap2d_kernel(double *A, long lon
     }
 }
 
-__global__ void __launch_bounds__(256) scatter_coo_kernel(double *A, long long ld, long long row0,
-                                                           long long rows, const int *irn,
-                                                           const int *jcn, const double *val,
-                                                           long long nz, int symmetric)
+// Matrix::read's densification (matrix.cc:12-21: A(i,j) = a, and A(j,i) = a when symmetric, in file
+// order, later entries overwriting) as three parallel passes.  The shard's own 8-byte cells hold
+// "index of the last writer + 1" between pass 1 and pass 3 (0 = untouched = the value 0.0).
+__device__ __forceinline__ unsigned long long *coo_cell(double *A, long long ld, long long row0, long long rows,
+                                                         long long i, long long j)
+{
+    return (i >= row0 && i < row0 + rows) ? reinterpret_cast<unsigned long long *>(A + (i - row0) * ld + j) : nullptr;
+}
+__global__ void __launch_bounds__(256) coo_claim_kernel(double *A, long long n, long long ld, long long row0,
+                                                         long long rows, const int *irn, const int *jcn,
+                                                         long long nz, int symmetric, int *bad)
 {
     const long long z = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= nz) return;
     const long long i = irn[z], j = jcn[z];
-    const double v = val[z];
-    if (i >= row0 && i < row0 + rows) A[(i - row0) * ld + j] = v;                  // matrix.cc:17
-    if (symmetric && j >= row0 && j < row0 + rows) A[(j - row0) * ld + i] = v;     // matrix.cc:18-20
+    if (i < 0 || j < 0 || i >= n || j >= n) {
+        *bad = 1;
+        return;
+    }
+    if (unsigned long long *cell = coo_cell(A, ld, row0, rows, i, j)) atomicMax(cell, (unsigned long long)z + 1ULL);
+    if (symmetric)
+        if (unsigned long long *cell = coo_cell(A, ld, row0, rows, j, i)) atomicMax(cell, (unsigned long long)z + 1ULL);
+}
+__global__ void __launch_bounds__(256) coo_winner_kernel(double *A, long long n, long long ld, long long row0,
+                                                          long long rows, const int *irn, const int *jcn,
+                                                          long long nz, int symmetric, unsigned char *win)
+{
+    const long long z = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= nz) return;
+    const long long i = irn[z], j = jcn[z];
+    unsigned char w = 0;
+    if (i >= 0 && j >= 0 && i < n && j < n) {
+        if (unsigned long long *cell = coo_cell(A, ld, row0, rows, i, j)) w |= (*cell == (unsigned long long)z + 1ULL) ? 1 : 0;
+        if (symmetric)
+            if (unsigned long long *cell = coo_cell(A, ld, row0, rows, j, i)) w |= (*cell == (unsigned long long)z + 1ULL) ? 2 : 0;
+    }
+    win[z] = w;
+}
+__global__ void __launch_bounds__(256) coo_store_kernel(double *A, long long ld, long long row0, const int *irn,
+                                                         const int *jcn, const double *val, long long nz,
+                                                         const unsigned char *win)
+{
+    const long long z = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= nz) return;
+    const unsigned char w = win[z];
+    const long long i = irn[z], j = jcn[z];
+    if (w & 1) A[(i - row0) * ld + j] = val[z];                                     // matrix.cc:17
+    if (w & 2) A[(j - row0) * ld + i] = val[z];                                     // matrix.cc:18-20
 }
 
 inline int grid_for(long long n) { return (int)((n + kChunk - 1) / kChunk); }
@@ -396,13 +433,15 @@ cudaError_t launch_generate_lap2d(double *A, long long n, long long ld, long lon
     return cudaGetLastError();
 }
 
-cudaError_t launch_scatter_coo(double *A, long long ld, long long row0, long long rows,
+cudaError_t launch_scatter_coo(double *A, long long n, long long ld, long long row0, long long rows,
                                const int *irn, const int *jcn, const double *val, long long nz,
-                               int symmetric, cudaStream_t s)
+                               int symmetric, unsigned char *win, int *bad, cudaStream_t s)
 {
     if (nz <= 0) return cudaSuccess;
-    scatter_coo_kernel<<<(int)((nz + 255) / 256), 256, 0, s>>>(A, ld, row0, rows, irn, jcn, val, nz,
-                                                               symmetric);
+    const int grid = (int)((nz + 255) / 256);
+    coo_claim_kernel<<<grid, 256, 0, s>>>(A, n, ld, row0, rows, irn, jcn, nz, symmetric, bad);
+    coo_winner_kernel<<<grid, 256, 0, s>>>(A, n, ld, row0, rows, irn, jcn, nz, symmetric, win);
+    coo_store_kernel<<<grid, 256, 0, s>>>(A, ld, row0, irn, jcn, val, nz, win);
     return cudaGetLastError();
 }
 

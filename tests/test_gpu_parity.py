@@ -68,6 +68,33 @@ def test_set_matrix_rows_and_coo_roundtrip(cgb, O, tmp_path):
         assert np.array_equal(ctx.get_matrix_rows(0, n), expect)
 
 
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_set_matrix_coo_million_random_duplicates(cgb, symmetric):
+    """Device-side densification with heavy cell collisions: 10^6 random triples into a 1500 x 1500
+    matrix (every cell is written ~0.4 / ~0.9 times on average, thousands of cells many times).  The
+    result must be the SEQUENTIAL loop of matrix.cc:12-21 -- the last entry in file order wins, the
+    mirror write of a symmetric entry included -- although the scatter runs in parallel."""
+    n, nz = 1500, 1_000_000
+    rng = _rng(11 + int(symmetric))
+    irn = rng.integers(0, n, nz, dtype=np.int32)
+    jcn = rng.integers(0, n, nz, dtype=np.int32)
+    val = rng.standard_normal(nz)
+    if symmetric:   # write order: (i, j) of entry 0, (j, i) of entry 0, (i, j) of entry 1, ...
+        cells = np.stack([irn.astype(np.int64) * n + jcn, jcn.astype(np.int64) * n + irn], axis=1).ravel()
+        vals = np.repeat(val, 2)
+    else:
+        cells, vals = irn.astype(np.int64) * n + jcn, val
+    u, first_in_reversed = np.unique(cells[::-1], return_index=True)
+    expect = np.zeros(n * n)
+    expect[u] = vals[len(cells) - 1 - first_in_reversed]
+    with _ctx(cgb, n) as ctx:
+        ctx.set_matrix_coo(irn, jcn, val, symmetric=symmetric)
+        assert np.array_equal(ctx.get_matrix_rows(0, n), expect.reshape(n, n))
+        with pytest.raises(cgb.CgbError):                       # an entry outside the matrix
+            ctx.set_matrix_coo(np.array([0, n], dtype=np.int32), np.array([0, 0], dtype=np.int32),
+                               np.array([1.0, 2.0]), symmetric=False)
+
+
 # --------------------------------------------------------------------------- kernels
 @pytest.mark.parametrize("n", [64, 1000, 2050, 4097])
 def test_gemv_every_variant_bitwise(cgb, O, n):
