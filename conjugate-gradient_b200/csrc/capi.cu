@@ -4,7 +4,7 @@
 // Multi-GPU design (replaces MPI_Allgatherv + 2 x MPI_Allreduce per iteration,
 // code/MPI/cg.cc:105-136): A is row-sharded by the reference's partition rule; the O(N) vectors
 // x, r, p are REPLICATED and updated redundantly by every rank, so the only exchange per
-// iteration is ONE all-gather of [Ap rows | p'Ap block partials] after the mat-vec.  The
+// iteration is ONE all-gather of the Ap rows after the mat-vec.  The
 // scalars (alpha, beta, r'r, the stop test) are then computed by every rank from identical
 // data in an identical order: bitwise equal on all ranks without any all-reduce.
 // Two implementations of that exchange (option "exchange"):
@@ -121,7 +121,7 @@ struct cgb_ctx {
     long long graph_replays = 0;   // graph launches since creation ("graph_replays", read-only option)
     int opt_balance = 1;           // persistent kernel: re-balance the rows between the CTAs from measured speeds
     long long aux_stride = 0;      // entries of one parity of the local LL side buffer
-    int opt_schedule = 1;          // 1: persistent cooperative kernel (persist.cu) when usable, 0: graph of 3 kernels
+    int opt_schedule = 1;          // 1: persistent cooperative kernel (persist.cu) when usable, 0: CUDA graph of 4 kernels per iteration
     long long spin_timeout_ms = 20000; // bound of the device-side waits on other CTAs / ranks
     PersistSync *psync = nullptr;
     uint4 *rr_ll = nullptr;        // [2][nchunks] LL entries of the r'r chunk partials
@@ -361,10 +361,9 @@ int persist_index(const cgb_ctx *c)
     return -1;
 }
 
-void persist_scratch(const cgb_ctx *c, int *qs_n, int *scr_n)
+void persist_scratch(const cgb_ctx *c, int *scr_n)
 {
     const long long scr = c->nchunks > c->nblk ? c->nchunks : c->nblk; // chunk partials / per-CTA timings
-    *qs_n = 0;
     *scr_n = (int)((scr + 1) & ~1LL);
 }
 
@@ -378,9 +377,9 @@ const char *persist_unusable(const cgb_ctx *c)
     const int pi = persist_index(c);
     if (pi < 0) return "no persistent instantiation of this tile shape";
     if (c->nchunks > (long long)persist_max_chunks() * c->nblk) return "N too large for the per-CTA vector chunks";
-    int qs_n, scr_n;
-    persist_scratch(c, &qs_n, &scr_n);
-    if (persist_variant(pi).smem_fixed() + (size_t)(qs_n + scr_n) * 8 + 4096 > (size_t)c->smem_optin) // + static
+    int scr_n;
+    persist_scratch(c, &scr_n);
+    if (persist_variant(pi).smem_fixed() + (size_t)scr_n * 8 + 4096 > (size_t)c->smem_optin) // + static
         return "tile ring + scratch exceed shared memory";
     return nullptr;
 }
@@ -420,7 +419,7 @@ int launch_persist(cgb_ctx *c, long long iters)
     a.iters = (int)iters;
     a.l2_prefetch = c->opt_l2_prefetch;
     a.balance = c->opt_balance;
-    persist_scratch(c, &a.qs_n, &a.scr_n);
+    persist_scratch(c, &a.scr_n);
     a.tol = c->tol;
     a.spin_ns = (unsigned long long)c->spin_timeout_ms * 1000000ULL;
     if (c->trace_cap > 0) a.trace = make_trace(c, 0, c->nblk);
@@ -915,7 +914,7 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
     } else if (k == "balance") {
         c->opt_balance = value != 0;
     } else if (k == "schedule") {
-        if (value != 0 && value != 1) return fail(CGB_ERR_INVALID, "schedule must be 0 (graph of 3 kernels) or 1 (persistent)");
+        if (value != 0 && value != 1) return fail(CGB_ERR_INVALID, "schedule must be 0 (CUDA graph of 4 kernels per iteration) or 1 (persistent kernel)");
         c->opt_schedule = (int)value;
     } else if (k == "spin_timeout_ms") {
         if (value < 1 || value > 3600000) return fail(CGB_ERR_INVALID, "spin_timeout_ms must be in [1, 3600000]");

@@ -33,7 +33,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), int grid, int block, 
 // ---- mat-vec (gemv.cu) --------------------------------------------------------------
 struct GemvVariant {
     const char *name;
-    int ctas_per_sm; // grid = sm_count * ctas_per_sm persistent CTAs (= p'Ap block partials)
+    int ctas_per_sm; // grid = sm_count * ctas_per_sm persistent CTAs
     int threads;
     cudaError_t (*launch)(const GemvArgs &a, int nblk, cudaStream_t s);
     cudaError_t (*preload)(); // load the kernel now (lazy module loading), not at its first launch

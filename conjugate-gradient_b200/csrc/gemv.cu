@@ -26,7 +26,7 @@
 
 namespace cgb {
 
-// One result (a row of Ap, or the block partial of p'Ap) into the gather buffer: locally, or --
+// One result (a row of Ap) into the gather buffer: locally, or --
 // fused exchange -- as a self-flagging LL entry straight into every rank's buffer over NVLink
 // (peer stores).  That store IS the all-gather: no fence, no flag, no collective kernel.
 // Called by ALL lanes of a warp with the same value: in fused mode lane g stores to rank g -- one

@@ -1,35 +1,40 @@
 // persist.cu -- the whole CG loop (code/MPI/cg.cc:96-137) as ONE persistent cooperative kernel.
 //
-// The three-kernel schedule (gemv.cu + vec.cu, CUDA graph + programmatic dependent launch)
-// serialises, every iteration, mat-vec -> x/r update -> p update -> mat-vec through kernel
-// boundaries; its %globaltimer timeline (profiles/r02/trace_*) shows ~11 us of such chain plus
-// ~5 us of start skew per iteration on the 8-way shard (5000 x 40000, 230 us of streaming).
-// Here one CTA per SM stays resident for the whole solve; the iteration's three data
-// dependencies -- the reference's MPI_Allgatherv + 2 x MPI_Allreduce (cg.cc:105-136) -- become
-// data-flow waits inside the kernel, and the producer warp never stops streaming A:
+// The graph schedule (gemv.cu + vec.cu: four kernels per iteration from a CUDA graph, chained
+// with programmatic dependent launch) serialises, every iteration, mat-vec -> vector updates ->
+// mat-vec through kernel boundaries; its %globaltimer timeline (profiles/r02/README.md) shows
+// ~11 us of such chain plus ~5 us of start skew per iteration on the 8-way shard (5000 x 40000,
+// 230 us of streaming).  Here one CTA per SM stays resident for all iterations; the iteration's
+// data dependencies -- the reference's MPI_Allgatherv + 2 x MPI_Allreduce (cg.cc:105-136) --
+// are data-flow waits inside the kernel, and the producer warp never stops streaming A:
 //
-//   phase M  mat-vec of this CTA's rows (the tile pipeline of gemv.cu, same summation order);
-//            every finished row and the CTA's p'Ap block partial go straight into EVERY rank's
-//            gather buffer as self-flagging LL entries (NVLink peer stores; also on 1 GPU).
-//   phase U  wait for all block partials of all ranks -> p'Ap, alpha; the CTA owns the
-//            256-element chunks c, c + grid, ... of the replicated vectors and keeps their
-//            x, r, p IN REGISTERS for the whole launch: x += alpha p, r -= alpha Ap (Ap polled
-//            from the LL entries), chunk partial of r'r -> rrpart[chunk], arrive on a counter.
-//   phase B  wait for all chunk partials -> r'r, stop test, beta; p = r + beta p for the own
-//            chunks, stored to the global p vector, arrive on a second counter.
-//   producer warp: meanwhile already has the A tiles of the next mat-vec in the shared-memory
-//            ring (A never changes) and more of them prefetched into L2; it waits for the p
-//            counter, then adds the p slices.  HBM keeps streaming across the iteration boundary.
+//   phase M  mat-vec of this CTA's rows (the tile pipeline of gemv.cu, same summation order, but
+//            with full stages for any rows-per-CTA ratio); every finished row goes straight into
+//            EVERY rank's gather buffer as a self-flagging LL entry (NVLink peer stores; the
+//            same entries are the intra-GPU synchronisation, so also on 1 GPU).
+//   phase U  the CTA owns the 256-element chunks c, c + grid, ... of the replicated vectors and
+//            keeps their x, r, p IN REGISTERS for the whole launch.  It polls the Ap entries of
+//            its chunks (rows of any CTA of any rank), publishes the chunk partials of p'Ap as LL
+//            entries, polls all of them -> p'Ap, alpha; x += alpha p, r -= alpha Ap; publishes the
+//            chunk partials of r'r.
+//   phase B  polls all r'r partials -> stop test, beta; p = r + beta p for the own chunks, stored
+//            to the global p vector, red.release on a counter.
+//   producer warp: meanwhile already has the first A tiles of the next mat-vec in the shared-
+//            memory ring (A never changes) and a few more prefetched into L2; ld.acquire on the p
+//            counter, fence.proxy.async, then the p slices.
+//   re-balancing: no reduction depends on which CTA computed a row, so the rows are
+//            re-partitioned between the CTAs from the mat-vec-phase times they publish (SMs differ
+//            persistently in the HBM bandwidth they obtain) -- without changing a result bit.
 //
-// Every reduction has the order of oracle/cg_oracle.c (row dot, block partials in (rank, block)
-// order, chunk256 partials of the global vector, det_sum), so the result is bitwise equal to the
-// three-kernel schedule and to the CPU oracle.  All scalars are computed redundantly by every
-// CTA of every rank from identical data: no all-reduce, no host round trip, no launch per
-// iteration; the kernel leaves the loop by itself on sqrt(r'r) < tol (cg.cc:120-121).
+// Every reduction has the order of oracle/cg_oracle.c (lane-order row dot; chunk256 partials of
+// the GLOBAL vector + det_sum for p'Ap and r'r alike), so the result is bitwise equal to the graph
+// schedule, to the CPU oracle, and the same for 1, 2, 4, 8 GPUs.  All scalars are computed
+// redundantly by every CTA of every rank from identical data: no all-reduce, no host round trip,
+// no launch per iteration; the kernel leaves the loop by itself on sqrt(r'r) < tol (cg.cc:120-121).
 //
 // CTAs wait on one another, so the launch is cooperative (co-residency is guaranteed or the
 // launch fails).  Ranks on other GPUs are waited for through the LL entries they write, exactly
-// as in the fused exchange of the three-kernel schedule.
+// as in the fused exchange of the graph schedule; every wait is bounded (spin_timeout_ms).
 #include "cgb_device.cuh"
 #include "cgb_kernels.h"
 
@@ -41,7 +46,7 @@ namespace {
 // A slot (a 16-row x 512 slot may be used as 8 rows x 1024), never less than the nominal width
 __host__ __device__ constexpr int persist_pmax(int slot, int tc) { return slot / 8 > tc ? slot / 8 : tc; }
 // 256-chunks of the replicated vectors one CTA can own (their x, r, p live in registers: 9 warps
-// leave 168 registers per thread): N <= 2 * 148 * 256 = 75776; larger systems take the 3-kernel schedule
+// leave 168 registers per thread): N <= 2 * 148 * 256 = 75776; larger systems take the graph schedule
 constexpr int kPersistMaxChunks = 2;
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
             ps[cc][e] = ok ? a.p[i] : 0.0;
         }
     }
-    // deferred book-keeping of the previous loop body (advance_state of the 3-kernel schedule):
+    // deferred book-keeping of the previous loop body (advance_state of the graph schedule):
     // rsold = r'r from the chunk partials the previous kernel left in rrpart
     for (unsigned t = tid; t < nchunks; t += NCT) scr[t] = a.rrpart[t];
     named_bar_sync(1, NCT);

@@ -1,5 +1,5 @@
-// vec.cu -- the O(N) part of the CG iteration, fused so that one iteration is three launches
-// (mat-vec, update_xr, update_p) with every scalar (alpha, beta, the stop test) on the device.
+// vec.cu -- the O(N) part of the CG iteration for the graph schedule: one iteration is four launches
+// (mat-vec, pap_partials, update_xr, update_p) with every scalar (alpha, beta, the stop test) on the device.
 // Replaces cblas_daxpy x3 + cblas_ddot x2 + MPI_Allreduce x2 (code/MPI/cg.cc:105-132) and
 // sumVec / fill / copy / cublasDdot + cudaMemcpy + cudaDeviceSynchronize (code/CUDA/cg.cu:
 // 112-164, 231-269).  All ranks hold the full-length x, r, p and run these kernels redundantly
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(32) finalize_kernel(const VecArgs a, long long
     }
 }
 
-// DEBUG block partials: d = A x - b ; d.d, b.b, x.x per chunk
+// DEBUG block (cg.cc:144-154), chunk partials: d = A x - b ; d.d, b.b, x.x per chunk
 __global__ void __launch_bounds__(kChunk) debug_partials_kernel(const VecArgs a, double *scratch,
                                                                  long long nchunks)
 {
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(kChunk) pap_plain_kernel(const double *v, cons
 }
 
 // Fused mode, test hooks only: consume the running exchange into the plain buffer (every rank's
-// rows and block partials), so that memcpys and sum_partials_kernel can read it.
+// rows), so that memcpys and pap_plain_kernel can read it.
 __global__ void __launch_bounds__(kChunk) exchange_collect_kernel(double *apx, const Gather g)
 {
     const int tid = threadIdx.x;

@@ -118,7 +118,7 @@ int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
  * "exchange": 0 ncclAllGather / 1 fused peer stores (see cgb_exchange_import);
  * "schedule": 1 (default) = the whole loop of cgb_iterate as ONE persistent cooperative kernel
  * (one CTA per SM stays resident, the iteration's dependencies are data-flow waits inside the
- * kernel, A streams across iteration boundaries), 0 = a CUDA graph of three kernels per
+ * kernel, A streams across iteration boundaries), 0 = a CUDA graph of four kernels per
  * iteration; bitwise identical results; "schedule_in_use" (read-only) tells which one the
  * current configuration gets (the persistent kernel needs the fused exchange, a 1-CTA-per-SM
  * variant, and is not used with "compat" / "profile");

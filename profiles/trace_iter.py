@@ -97,7 +97,7 @@ def summarize(g, xr, p, rows, n, skip=4):
 
 def summarize_persistent(g, rows, n, skip=4):
     """g: [L, nblk, 8] records of the persistent kernel (one per iteration and CTA): 0 iteration
-    start, 3 first tile consumed, 5 rows + block partial stored, 1 alpha known, 2 own r'r partials
+    start, 3 first tile consumed, 5 rows stored, 1 alpha known, 2 own r'r partials
     published, 4 beta known, 6 own p chunks published."""
     g = g.astype(np.int64)
     L = g.shape[0]

@@ -51,7 +51,7 @@ def test_bench_line_small_system():
 
 
 def test_bench_line_graph_schedule():
-    """--schedule 0: the three-kernel CUDA graph; the roofline kernel is then the mat-vec."""
+    """--schedule 0: the CUDA graph of four kernels per iteration; the roofline kernel is then the mat-vec."""
     d = _bench("--size", "4096", "--iters", "50", "--steps", "3", "--warmup", "3", "--no-cpu-baseline",
                "--schedule", "0")
     # 4 launches per iteration (mat-vec, p'Ap partials, update_xr, update_p) + init (2) + finalize (1) per step

@@ -98,7 +98,7 @@ def test_set_matrix_coo_million_random_duplicates(cgb, symmetric):
 # --------------------------------------------------------------------------- kernels
 @pytest.mark.parametrize("n", [64, 1000, 2050, 4097])
 def test_gemv_every_variant_bitwise(cgb, O, n):
-    """Every mat-vec variant == the oracle's lane-order row dot, bit for bit; block partials
+    """Every mat-vec variant == the oracle's lane-order row dot, bit for bit; chunk partials
     and their deterministic total likewise."""
     rng = _rng(n)
     A = rng.standard_normal((n, n))
@@ -166,7 +166,7 @@ def _solve_gpu(cgb, n, setup, max_iter, variant=None, graph=1, x0=None, schedule
 def test_solve_generated_bitwise_vs_oracle(cgb, O, n, max_iter, sched):
     """Whole solve == oracle bit for bit: iteration count, every r'r, final x, DEBUG numbers --
     under every schedule of the loop: ONE persistent cooperative kernel (csrc/persist.cu, the
-    default), a CUDA graph of three kernels per iteration, plain launches."""
+    default), a CUDA graph of four kernels per iteration, plain launches."""
     b = O.init_source_term(n)
 
     def setup(ctx):
@@ -239,7 +239,7 @@ def test_persistent_schedule_ragged_sizes_every_shape(cgb, O, n):
 
 
 def test_schedules_interleave_bitwise(cgb, O):
-    """cgb_iterate in pieces, alternating the persistent kernel and the three-kernel graph on the
+    """cgb_iterate in pieces, alternating the persistent kernel and the graph schedule on the
     same solve: the state handed over between launches (x, r, p, r'r partials, k) is complete,
     so any split gives the bits of one uninterrupted solve."""
     n = 3000
@@ -370,7 +370,7 @@ def test_n_beyond_int32_indexing(cgb, O):
 def test_compat_topologies_bitwise_vs_oracle(cgb, O, nt, bw):
     """Option "compat": the reference's column (MatVecT) and row (MatVec) launch topologies with
     NUM_THREADS / BLOCK_WIDTH literal (csrc/compat.cu).  Both give the oracle's chunked order
-    bit for bit -- mat-vec, block partials and a whole solve -- for any launch shape, where the
+    bit for bit -- mat-vec, chunk partials and a whole solve -- for any launch shape, where the
     reference's atomicAdd version is run-to-run non-deterministic."""
     n = 1030
     rng = _rng(bw)
