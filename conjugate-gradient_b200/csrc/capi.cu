@@ -580,7 +580,7 @@ extern "C" int cgb_create(int64_t n, int rank, int world, int device, cgb_ctx **
     CKB(cudaMalloc(&c->scratch, (size_t)(3 * c->nchunks + 8) * sizeof(double)));
     CKB(cudaMalloc(&c->sink, 64));
     CKB(cudaMalloc(&c->st, sizeof(State)));
-    CKB(cudaHostAlloc(&c->h_done, sizeof(int), cudaHostAllocMapped));
+    CKB(cudaHostAlloc(&c->h_done, 8 * sizeof(int), cudaHostAllocMapped)); // [0] flag, [1..6] context of a timeout report
     CKB(cudaHostGetDevicePointer(&c->d_hdone, c->h_done, 0));
     CKB(cudaHostAlloc(&c->h_pin, 64 * sizeof(double), cudaHostAllocDefault));
     *c->h_done = 0;
@@ -1106,9 +1106,12 @@ extern "C" int cgb_iterate(cgb_ctx *c, int64_t iters, float *ms)
         if (e != cudaSuccess) {
             const int code = *(volatile int *)c->h_done;
             if (code < 0)
-                return fail(CGB_ERR_TIMEOUT, "a device-side wait (kind %d: 1 = peer rank's mat-vec rows, 2 = local "
-                            "mat-vec, 3 = r'r partials, 4 = p chunks) exceeded spin_timeout_ms = %lld: a rank is "
-                            "missing or stuck (%s)", -code, c->spin_timeout_ms, cudaGetErrorString(e));
+                return fail(CGB_ERR_TIMEOUT, "a device-side wait (kind %d: 1 = an LL entry -- a peer rank's mat-vec rows or a chunk "
+                            "partial, 4 = p chunks, 5 = tile for the consumers, 6 / 9 = row partition hand-over, 7 = free "
+                            "pipeline stage, 8 = drain) exceeded spin_timeout_ms = %lld: a rank is "
+                            "missing or stuck (%s) [cta %d thread %d: %d %d %d %d]", -code, c->spin_timeout_ms,
+                            cudaGetErrorString(e), c->h_done[1], c->h_done[2], c->h_done[3], c->h_done[4], c->h_done[5],
+                            c->h_done[6]);
             CK(e);
         }
         float t = 0.f;
@@ -1404,7 +1407,7 @@ extern "C" int cgb_autotune(cgb_ctx *c, int iters, int *chosen, float *us_per_it
     if (rc) return rc;
     if (c->in_solve) return fail(CGB_ERR_STATE, "solve in progress");
     if (!c->matrix_set) return fail(CGB_ERR_STATE, "matrix not set");
-    if (iters < 1) iters = 12;
+    if (iters < 1) iters = 32; // long enough for the row re-balancing to act on every shape alike
     const int nv = gemv_variant_count();
     if (us_per_iter)
         for (int v = 0; v < nv; ++v) us_per_iter[v] = -1.f;

@@ -87,10 +87,20 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const uint4 *p)
 
 // A wait that can only end badly is reported before it faults the launch: the host finds the
 // code in the mapped flag and returns CGB_ERR_TIMEOUT instead of a bare "unspecified failure".
-__device__ __noinline__ void spin_timeout(const PersistArgs &a, int what)
+__device__ __noinline__ void spin_timeout(const PersistArgs &a, int what, int d0 = 0, int d1 = 0, int d2 = 0,
+                                          int d3 = 0)
 {
     if (a.host_done) {
-        *a.host_done = -(what);
+        if (*(volatile int *)a.host_done >= 0) { // (racy on purpose) an early report; context for the message
+            a.host_done[1] = (int)blockIdx.x;
+            a.host_done[2] = (int)threadIdx.x;
+            a.host_done[3] = d0;
+            a.host_done[4] = d1;
+            a.host_done[5] = d2;
+            a.host_done[6] = d3;
+            __threadfence_system();
+            *a.host_done = -(what);
+        }
         __threadfence_system();
     }
     __trap();
@@ -164,12 +174,13 @@ __device__ __forceinline__ void prefetch_l2_line(const void *p)
 }
 
 // mbarrier wait with the configurable bound (a peer rank may legitimately be seconds late)
-__device__ __forceinline__ void mbar_wait_ns(const PersistArgs &a, uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait_ns(const PersistArgs &a, uint64_t *bar, uint32_t parity, int what,
+                                             int d0 = 0, int d1 = 0, int d2 = 0, int d3 = 0)
 {
     if (mbar_try_wait(bar, parity)) return;
     const unsigned long long t0 = globaltimer_ns();
     while (!mbar_try_wait(bar, parity)) {
-        if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 5);
+        if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, what, d0, d1, d2, d3);
     }
 }
 
@@ -304,7 +315,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                 bulk_g2s(sP + (size_t)stage * PMAX, a.p + s_c0[stage], (unsigned)(s_w[stage] * 8), &full[stage], pol_p);
         };
         auto wait_empty = [&](unsigned g) {
-            if (g >= (unsigned)STAGES) mbar_wait_ns(a, &empty[g % STAGES], ((g / STAGES) & 1u) ^ 1u);
+            if (g >= (unsigned)STAGES) mbar_wait_ns(a, &empty[g % STAGES], ((g / STAGES) & 1u) ^ 1u, 7, (int)g);
         };
         Geo ge = geo_of(0);
         Cur cur;
@@ -331,7 +342,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                 stop = __shfl_sync(0xffffffffu, stop, 0);
                 if (stop) {
                     for (unsigned u = 0; u < pre; ++u) issueP(gbase + u);
-                    for (unsigned u = 0; u < pre; ++u) mbar_wait_ns(a, &full[(gbase + u) % STAGES], ((gbase + u) / STAGES) & 1u);
+                    for (unsigned u = 0; u < pre; ++u)
+                        mbar_wait_ns(a, &full[(gbase + u) % STAGES], ((gbase + u) / STAGES) & 1u, 8, m, (int)gbase, (int)pre,
+                                     (int)ge.T);
                     return;
                 }
             }
@@ -346,16 +359,21 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
             pre = 0;
             if (m + 1 < a.iters) {
                 // the row range of the next mat-vec (re-balanced two iterations ago) ...
+                int stop = 0;
                 if (lane == 0) {
                     const unsigned long long t0 = globaltimer_ns();
                     while (s_part_seq < m + 1 && !s_stop) {
                         __nanosleep(64);
                         if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 6);
                     }
+                    stop = s_stop;
                 }
-                __syncwarp();
+                // ONE lane decides for the warp: s_stop may be raised at this very moment, and lanes that
+                // read it themselves could disagree -- part of the warp (lane 0, which arms the barriers,
+                // perhaps among them) would leave while the rest went on issuing copies
+                stop = __shfl_sync(0xffffffffu, stop, 0);
                 __threadfence_block();
-                if (s_stop) return; // nothing in flight: all steps of mat-vec m were consumed or the loop never reached it
+                if (stop) return; // nothing in flight: all steps of mat-vec m were consumed or the loop never reached it
                 ge = geo_of(m + 1);
                 cur_block(cur, ge, 0);
                 __syncwarp();
@@ -520,7 +538,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                 const unsigned ph = (g / STAGES) & 1u;
                 const long long c0 = (long long)t * wd;
                 const int w = (int)((a.ld - c0 < wd) ? (a.ld - c0) : wd);
-                mbar_wait_ns(a, &full[stage], ph);
+                mbar_wait_ns(a, &full[stage], ph, 5, m, (int)g, b, t);
                 if (tid == 0 && b == 0 && t == 0) {
                     tm0 = globaltimer_ns();
                     if (rec) rec[3] = tm0;
@@ -658,7 +676,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                     const unsigned long long t0 = globaltimer_ns();
                     while (s_prod_geo < m) {
                         __nanosleep(64);
-                        if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 6);
+                        if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 9);
                     }
                 }
                 __syncwarp();

@@ -139,7 +139,7 @@ int cgb_gemv_variant_count(void);
 const char *cgb_gemv_variant_name(int variant);
 
 /* One-off choice of the mat-vec tile shape ("gemv_variant") for this rank's shard shape on this
- * GPU: every candidate shape runs `iters` (<= 0: 12) loop bodies of the schedule in use on the
+ * GPU: every candidate shape runs `iters` (<= 0: 32) loop bodies of the schedule in use on the
  * resident matrix, the fastest becomes the configured variant.  Call it after the matrix is
  * set and OUTSIDE any timed region (the reference's timer brackets solve() only,
  * code/MPI/cg_main.cc:53-55).  A rank of world > 1 tunes alone (its exchange looped back to

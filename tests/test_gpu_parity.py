@@ -365,6 +365,36 @@ def test_n_beyond_int32_indexing(cgb, O):
     assert abs(nx - np.linalg.norm(x)) <= 1e-12 * nx
 
 
+def test_persistent_schedule_size_limit_and_fallback(cgb, O):
+    """The persistent kernel keeps the vector chunks of a CTA in registers: it takes N up to
+    2 * 148 * 256 = 75776; one more and cgb_iterate falls back to the graph schedule by itself.  At
+    the limit (46 GB of A, 64-bit indexing, two chunks per CTA) both schedules give the same bits,
+    and the recursive residual equals the true residual the DEBUG block recomputes."""
+    n = 75776
+    b = cgb.init_source_term(n)
+    out = {}
+    with _ctx(cgb, n) as ctx:
+        if ctx.layout().sm_count != 148:
+            pytest.skip("limit is stated for 148 SMs")
+        ctx.generate_lap2d()
+        ctx.set_rhs(b)
+        for sched in (1, 0):
+            ctx.set_option("schedule", sched)
+            assert ctx.get_option("schedule_in_use") == sched
+            x = np.zeros(n)
+            info, hist = ctx.solve(x, max_iter=24, tol=1e-10, history=True)
+            nx, rr = ctx.residual_check()
+            out[sched] = (x, hist, info.k, nx, rr)
+    assert out[1][2] == out[0][2] == 24
+    assert np.array_equal(out[1][1], out[0][1]) and np.array_equal(out[1][0], out[0][0])
+    assert out[1][3:] == out[0][3:]
+    true_resid = out[1][4] * np.linalg.norm(b)
+    assert abs(true_resid - np.sqrt(out[1][1][-1])) <= 1e-9 * true_resid
+    with _ctx(cgb, n + 1) as ctx:
+        ctx.set_option("schedule", 1)
+        assert ctx.get_option("schedule_in_use") == 0     # falls back: too many chunks per CTA
+
+
 # --------------------------------------------------------------------------- reference topologies
 @pytest.mark.parametrize("nt,bw", [(32, 1), (64, 16), (1000, 4096), (7, 5), (256, 1024)])
 def test_compat_topologies_bitwise_vs_oracle(cgb, O, nt, bw):
