@@ -112,6 +112,9 @@ int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
  * "num_threads"/"block_width": the NUM_THREADS / BLOCK_WIDTH command-line knobs of the
  * reference CUDA program (code/CUDA/cg_main.cc:21-25), mapped onto threads per CTA and
  * column-tile width of the mat-vec; "graph": 0/1 CUDA-graph replay of the iteration;
+ * "poll_every" / "graph_unroll": graph schedule only -- iterations between two looks at the stop flag and
+ * iterations per graph (the instantiated graph holds min of the two; "graph_replays", read-only,
+ * counts its launches);
  * "pdl": 0/1 programmatic dependent launch between the kernels of the iteration (the next
  * mat-vec prefetches A while the vector updates still run); "l2_prefetch": pipeline steps of A
  * the mat-vec additionally pulls into L2 before that wait (0 = off);
@@ -124,6 +127,8 @@ int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
  * variant, and is not used with "compat" / "profile");
  * "spin_timeout_ms": bound of the device-side waits on other ranks (default 20000); when it
  * expires the call returns CGB_ERR_TIMEOUT (the context is then unusable);
+ * "balance": 1 (default) = the persistent kernel re-partitions the rows between its CTAs from the
+ * mat-vec times they measure (no result bit depends on the partition);
  * "trace": launches kept by the diagnostic timeline (cgb_trace_read; 0 = off);
  * "loopback": profiling aid -- a rank of world > 1 with no peers aims every peer pointer of the
  * fused exchange at its own buffer, so ONE GPU runs one rank's shard under the production
