@@ -244,7 +244,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nblk = gridDim.x, c = blockIdx.x;
-    const bool balance = a.balance != 0 && nblk <= kMaxGrid;
+    // re-balancing moves whole rows: worth it from ~64 rows per CTA on (one row = 1.5 % of a CTA's work);
+    // below that its granularity is coarser than the imbalance it removes (measured: -0.5 % at 34 rows)
+    const bool balance = a.balance != 0 && nblk <= kMaxGrid && a.rows >= 64LL * nblk;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {

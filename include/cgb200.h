@@ -128,7 +128,7 @@ int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
  * "spin_timeout_ms": bound of the device-side waits on other ranks (default 20000); when it
  * expires the call returns CGB_ERR_TIMEOUT (the context is then unusable);
  * "balance": 1 (default) = the persistent kernel re-partitions the rows between its CTAs from the
- * mat-vec times they measure (no result bit depends on the partition);
+ * mat-vec times they measure, when a CTA has at least 64 rows (no result bit depends on the partition);
  * "trace": launches kept by the diagnostic timeline (cgb_trace_read; 0 = off);
  * "loopback": profiling aid -- a rank of world > 1 with no peers aims every peer pointer of the
  * fused exchange at its own buffer, so ONE GPU runs one rank's shard under the production
