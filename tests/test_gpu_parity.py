@@ -365,6 +365,25 @@ def test_n_beyond_int32_indexing(cgb, O):
     assert abs(nx - np.linalg.norm(x)) <= 1e-12 * nx
 
 
+def test_row_rebalancing_changes_no_bit(cgb, O):
+    """The persistent kernel re-partitions the rows between its CTAs from measured mat-vec times (from
+    64 rows per CTA on: n >= 9472 on 148 SMs) -- a timing-dependent choice.  No reduction depends on
+    row ownership, so the run with re-balancing, the run without and the oracle agree bit for bit."""
+    n, iters = 9600, 48
+    A, b = O.generate_lap2d(n), O.init_source_term(n)
+    ref = O.solve(A, b, max_iter=iters, nranks=1, nblk=148)
+    with _ctx(cgb, n) as ctx:
+        ctx.generate_lap2d()
+        ctx.set_rhs(b)
+        ctx.set_option("schedule", 1)
+        for balance in (1, 0, 1):
+            ctx.set_option("balance", balance)
+            x = np.zeros(n)
+            info, hist = ctx.solve(x, max_iter=iters, tol=1e-10, history=True)
+            assert info.k == ref.k == iters
+            assert np.array_equal(hist, ref.hist) and np.array_equal(x, ref.x), balance
+
+
 def test_persistent_schedule_size_limit_and_fallback(cgb, O):
     """The persistent kernel keeps the vector chunks of a CTA in registers: it takes N up to
     2 * 148 * 256 = 75776; one more and cgb_iterate falls back to the graph schedule by itself.  At
