@@ -1440,6 +1440,9 @@ extern "C" int cgb_autotune(cgb_ctx *c, int iters, int *chosen, float *us_per_it
     drop_graph(c);
     int best = keep_variant;
     float best_us = -1.f, default_us = -1.f;
+    // the timed runs; a lambda so that a failing CUDA call still reaches the restore below
+    auto tune = [&]() -> int {
+    int rc = CGB_OK;
     for (int v = 0; v < nv && rc == CGB_OK; ++v) {
         if (strncmp(gemv_variant(v).name, "tma", 3) != 0 || strstr(gemv_variant(v).name, "nohint")) continue;
         set_variant(c, v);
@@ -1475,6 +1478,9 @@ extern "C" int cgb_autotune(cgb_ctx *c, int iters, int *chosen, float *us_per_it
             best = v;
         }
     }
+    return rc;
+    };
+    rc = tune();
     // a candidate must beat the configured shape by more than the run-to-run noise
     if (default_us > 0.f && best_us > default_us * 0.997f) best = keep_variant;
     // leave no trace: state, exchange epoch; the LL entries of the looped-back runs go with the scratch
