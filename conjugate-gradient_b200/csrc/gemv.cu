@@ -21,6 +21,8 @@
 // grid reduction that replaces the reference's atomicAdd): no reduction depends on which CTA,
 // SM or GPU computed a row, so rows can be re-balanced freely without changing a bit.
 // Block 0 also performs the scalar bookkeeping of the previous iteration (advance_state).
+#include <cuda.h> // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include "cgb_device.cuh"
 #include "cgb_kernels.h"
 
@@ -43,11 +45,38 @@ __device__ __forceinline__ void store_out(const GemvArgs &a, long long plain_off
 }
 
 // ------------------------------------------------------------------------------- TMA
-template <int CW, int RPW, int TC, int STAGES, int MINB, int POL>
-__global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const GemvArgs a)
+// POL 0: 1-D bulk copies (one per tile row) with L2 hints -- the product path.
+// POL 1: the same without hints.
+// POL 2: the A/B the 1-D choice is measured against -- tiled copies through a 2-D tensor map
+//        (cp.async.bulk.tensor.2d -> SASS UTMALDG), one [TR x 256] box per instruction (256 is the
+//        largest box edge a tensor map allows), boxes side by side in the stage.
+constexpr int kBoxCols = 256;
+
+__device__ __forceinline__ void tensor_g2s_2d(void *dst_smem, const void *tmap, int x, int y, uint64_t *bar,
+                                              uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst_smem)),
+        "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// where 128-bit chunk q of tile row `row` sits in a stage: row-major [TR][TC], or -- tensor map --
+// box-major [TC/256][TR][256]
+template <int TR, int TC, int POL>
+__device__ __forceinline__ int tile_index(int row, int q)
+{
+    if (POL == 2) return (q / (kBoxCols / 2)) * (TR * (kBoxCols / 2)) + row * (kBoxCols / 2) + (q % (kBoxCols / 2));
+    return row * (TC / 2) + q;
+}
+
+template <int CW, int RPW, int TC, int STAGES, int POL>
+__device__ __forceinline__ void gemv_tma_body(const GemvArgs &a, const void *tmap)
 {
     constexpr int TR = CW * RPW;
     static_assert(TC % 64 == 0, "tile width must be a multiple of 64 doubles");
+    static_assert(POL != 2 || TC % kBoxCols == 0, "tensor-map tiles are whole boxes wide");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sA = reinterpret_cast<double *>(smem_raw);            // [STAGES][TR][TC]
     double *sP = sA + (size_t)STAGES * TR * TC;                   // [STAGES][TC]
@@ -97,7 +126,19 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
             const int stage = it % STAGES;
             const long long c0 = (long long)t * TC;
             const int w = (int)((a.ld - c0 < TC) ? (a.ld - c0) : TC);
-            if (partA) {
+            if (partA && POL == 2) {
+                // whole boxes: rows past nr belong to the next row block (or are zero-filled past
+                // the shard), columns past ld are zero-filled; the barrier counts full boxes
+                const int nbox = (w + kBoxCols - 1) / kBoxCols;
+                if (lane == 0)
+                    mbar_arrive_expect_tx(&full[stage], (unsigned)(nbox * TR * kBoxCols * 8 + w * 8));
+                __syncwarp();
+                double *dstA = sA + (size_t)stage * TR * TC;
+                if (lane == 0) // the descriptor path is warp-uniform: one elected lane issues the boxes
+                    for (int j = 0; j < nbox; ++j)
+                        tensor_g2s_2d(dstA + (size_t)j * TR * kBoxCols, tmap, (int)(c0 + (long long)j * kBoxCols),
+                                      (int)rb0, &full[stage], pol_a);
+            } else if (partA) {
                 if (lane == 0) mbar_arrive_expect_tx(&full[stage], (unsigned)((nr + 1) * w * 8));
                 __syncwarp();
                 double *dstA = sA + (size_t)stage * TR * TC;
@@ -181,7 +222,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
                         const double2 pv = sp2[q];
 #pragma unroll
                         for (int s = 0; s < RPW; ++s) {
-                            const double2 av = sa2[(warp + s * CW) * (TC / 2) + q];
+                            const double2 av = sa2[tile_index<TR, TC, POL>(warp + s * CW, q)];
                             acc0[s] = __fma_rn(av.x, pv.x, acc0[s]);
                             acc1[s] = __fma_rn(av.y, pv.y, acc1[s]);
                         }
@@ -193,7 +234,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
 #pragma unroll
                         for (int s = 0; s < RPW; ++s) {
                             if (s < nv) {
-                                const double2 av = sa2[(warp + s * CW) * (TC / 2) + q];
+                                const double2 av = sa2[tile_index<TR, TC, POL>(warp + s * CW, q)];
                                 acc0[s] = __fma_rn(av.x, pv.x, acc0[s]);
                                 acc1[s] = __fma_rn(av.y, pv.y, acc1[s]);
                             }
@@ -218,6 +259,19 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const Gem
             trace_stamp(rec, 6);
         }
     }
+}
+
+template <int CW, int RPW, int TC, int STAGES, int MINB, int POL>
+__global__ void __launch_bounds__((CW + 1) * 32, MINB) gemv_tma_kernel(const GemvArgs a)
+{
+    gemv_tma_body<CW, RPW, TC, STAGES, POL>(a, nullptr);
+}
+
+template <int CW, int RPW, int TC, int STAGES>
+__global__ void __launch_bounds__((CW + 1) * 32, 1)
+    gemv_tensormap_kernel(const GemvArgs a, const __grid_constant__ CUtensorMap tmap)
+{
+    gemv_tma_body<CW, RPW, TC, STAGES, 2>(a, &tmap);
 }
 
 // ------------------------------------------------------------------------------- LDG
@@ -336,6 +390,54 @@ cudaError_t tma_preload()
     return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)tma_smem<CW, RPW, TC, STAGES>(0));
 }
+// ---- tensor-map variant: the descriptor of the shard, encoded per launch (a few hundred ns on
+// the host; a captured graph keeps its copy)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+template <int CW, int RPW, int TC, int STAGES>
+cudaError_t tensormap_launch(const GemvArgs &a, int nblk, cudaStream_t s)
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return cudaErrorNotSupported;
+    alignas(64) CUtensorMap tm;
+    const cuuint64_t gdim[2] = {(cuuint64_t)a.ld, (cuuint64_t)a.rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)a.ld * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)kBoxCols, (cuuint32_t)(CW * RPW)};
+    const cuuint32_t estride[2] = {1, 1};
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(a.A), gdim, gstride, box, estride,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    const size_t smem = tma_smem<CW, RPW, TC, STAGES>(0);
+    auto k = gemv_tensormap_kernel<CW, RPW, TC, STAGES>;
+    return launch_kernel(k, nblk, (CW + 1) * 32, smem, s, a.pdl != 0, a, tm);
+}
+template <int CW, int RPW, int TC, int STAGES>
+cudaError_t tensormap_preload()
+{
+    cudaFuncAttributes fa;
+    auto k = gemv_tensormap_kernel<CW, RPW, TC, STAGES>;
+    cudaError_t e = cudaFuncGetAttributes(&fa, k);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)tma_smem<CW, RPW, TC, STAGES>(0));
+}
+
 template <int W, int RPW, int UNR>
 cudaError_t ldg_preload()
 {
@@ -370,6 +472,11 @@ const GemvVariant kVariants[] = {
     {"ldg_w8r2u4", 4, 256, ldg_launch<8, 2, 4>, ldg_preload<8, 2, 4>},
     {"ldg_w16r4u2", 2, 512, ldg_launch<16, 4, 2>, ldg_preload<16, 4, 2>},
     {"tma_w4r1c2048s2", 1, 160, tma_launch<4, 1, 2048, 2, 1>, tma_preload<4, 1, 2048, 2, 1>},
+    // 2-D tensor-map producer, for the A/B against the 1-D bulk copies (profiles/r02/tensormap_ab.md);
+    // same summation order, same bits.  Not a candidate of cgb_autotune.
+    {"tm2d_w8r1c1024s3", 1, 288, tensormap_launch<8, 1, 1024, 3>, tensormap_preload<8, 1, 1024, 3>},
+    {"tm2d_w8r2c512s3", 1, 288, tensormap_launch<8, 2, 512, 3>, tensormap_preload<8, 2, 512, 3>},
+    {"tm2d_w4r4c512s3", 1, 160, tensormap_launch<4, 4, 512, 3>, tensormap_preload<4, 4, 512, 3>},
 };
 
 } // namespace

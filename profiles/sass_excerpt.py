@@ -15,11 +15,13 @@ KERNELS = [
      "cg_persist_kernel<8,2,512,3> -- the whole CG loop, one cooperative launch (csrc/persist.cu)"),
     ("_ZN3cgb15gemv_tma_kernelILi8ELi2ELi512ELi3ELi1ELi0EEEvNS_8GemvArgsE",
      "gemv_tma_kernel<8,2,512,3> -- mat-vec of the graph schedule, init and DEBUG mat-vecs (csrc/gemv.cu)"),
+    ("_ZN3cgb21gemv_tensormap_kernelILi8ELi1ELi1024ELi3EEEvNS_8GemvArgsE14CUtensorMap_st",
+     "gemv_tensormap_kernel<8,1,1024,3> -- the A/B arm only: 2-D tensor-map producer (profiles/r02/tensormap_ab.md)"),
 ]
 WHAT = [
     ("UBLKCP", "cp.async.bulk.shared::cluster.global.mbarrier (1-D TMA bulk copy of a tile row / p slice)"),
     ("UBLKPF", "cp.async.bulk.prefetch.L2 (A tiles of the next mat-vec into L2)"),
-    ("UTMALDG", "cp.async.bulk.tensor (tensor-map TMA) -- not used: rows of a tile are copied as 1-D bulk rows"),
+    ("UTMALDG", "cp.async.bulk.tensor.2d (tensor-map TMA) -- only in the tm2d_* A/B variants; the product copies tile rows as 1-D bulk rows"),
     ("SYNCS", "mbarrier init / arrive / expect_tx / try_wait"),
     ("LDS.128", "128-bit shared-memory loads of A and p (conflict-free: lane l reads chunk l, l+32, ...)"),
     ("DFMA", "fp64 FMA -- CUDA cores; no tensor-core instruction (HMMA/UTC*MMA) in an HBM-bound GEMV"),
@@ -48,7 +50,7 @@ def main():
             n = sum(1 for t in text if key in t)
             print("| `%s` | %d | %s |" % (key, n, what))
         print()
-        for key in ("UBLKCP", "UBLKPF", "STG.E.128.STRONG.SYS", "LDG.E.128.STRONG.SYS", "REDG.E.ADD", "FENCE.VIEW.ASYNC"):
+        for key in ("UBLKCP", "UTMALDG", "UBLKPF", "STG.E.128.STRONG.SYS", "LDG.E.128.STRONG.SYS", "REDG.E.ADD", "FENCE.VIEW.ASYNC"):
             hits = [i for i, t in enumerate(text) if key in t]
             if not hits:
                 continue
