@@ -116,7 +116,7 @@ struct cgb_ctx {
     int opt_compat = 0;            // 1: the reference's mat-vec topologies (compat.cu)
     double *compat_part = nullptr; // chunk partials of the compat mat-vec
     size_t compat_part_cap = 0;
-    int poll_every = 16, graph_unroll = 16, opt_pdl = 1, opt_l2_prefetch = 4;
+    int poll_every = 16, graph_unroll = 16, opt_pdl = 1, opt_l2_prefetch = 4, opt_l2_ramp = 2;
     int graph_len = 0;             // iterations in the instantiated graph (min(graph_unroll, poll_every))
     long long graph_replays = 0;   // graph launches since creation ("graph_replays", read-only option)
     int opt_balance = 1;           // persistent kernel: re-balance the rows between the CTAs from measured speeds
@@ -418,6 +418,7 @@ int launch_persist(cgb_ctx *c, long long iters)
     a.world = c->world;
     a.iters = (int)iters;
     a.l2_prefetch = c->opt_l2_prefetch;
+    a.l2_ramp = c->opt_l2_ramp;
     a.balance = c->opt_balance;
     persist_scratch(c, &a.scr_n);
     a.tol = c->tol;
@@ -907,6 +908,9 @@ extern "C" int cgb_set_option(cgb_ctx *c, const char *key, int64_t value)
     } else if (k == "pdl") {
         c->opt_pdl = value != 0;
         drop_graph(c);
+    } else if (k == "l2_ramp") {
+        if (value < 0 || value > 64) return fail(CGB_ERR_INVALID, "l2_ramp must be in [0, 64] pipeline steps");
+        c->opt_l2_ramp = (int)value;
     } else if (k == "l2_prefetch") {
         if (value < 0 || value > 64) return fail(CGB_ERR_INVALID, "l2_prefetch must be in [0, 64] pipeline steps");
         c->opt_l2_prefetch = (int)value;
@@ -997,6 +1001,7 @@ extern "C" int cgb_get_option(cgb_ctx *c, const char *key, int64_t *value)
     else if (k == "compat") *value = c->opt_compat;
     else if (k == "pdl") *value = c->opt_pdl;
     else if (k == "l2_prefetch") *value = c->opt_l2_prefetch;
+    else if (k == "l2_ramp") *value = c->opt_l2_ramp;
     else if (k == "exchange") *value = c->opt_exchange;
     else if (k == "trace") *value = c->trace_cap;
     else if (k == "schedule") *value = c->opt_schedule;

@@ -112,7 +112,7 @@ struct PersistArgs {
     double *hist;              // nullable
     int *host_done;            // mapped pinned flag: 1 = converged, < 0 = a wait timed out
     long long ld, rows, row0, n, maxrows, n_loc, slot, bufstride, slot_off, nchunks;
-    int rank, world, iters, l2_prefetch, balance;
+    int rank, world, iters, l2_prefetch, l2_ramp, balance;
     int scr_n;                 // shared-memory scratch: doubles for the chunk partials being summed
     double tol;
     unsigned long long spin_ns; // bound of every cross-CTA / cross-rank wait

@@ -351,6 +351,20 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                 }
             }
             for (unsigned u = 0; u < pre; ++u) issueP(gbase + u);
+            if (a.l2_ramp > 0 && m > 0) {
+                // the steps already on chip (ring + L2) are consumed faster than HBM delivers: keep HBM
+                // busy meanwhile with the steps after them
+                Cur pf = cur;
+                unsigned u = pre;
+                for (int q = 0; q < a.l2_prefetch && u < ge.T; ++q, ++u) cur_next(pf, ge);
+                for (int q = 0; q < a.l2_ramp && u < ge.T; ++q, ++u) {
+                    const long long c0 = (long long)pf.t * pf.wdb;
+                    const int w = (int)((a.ld - c0 < pf.wdb) ? (a.ld - c0) : pf.wdb);
+                    for (int j = lane; j < pf.nr; j += 32)
+                        bulk_prefetch_l2(a.A + (pf.rb0 + j) * a.ld + c0, (unsigned)(w * 8));
+                    cur_next(pf, ge);
+                }
+            }
             for (unsigned g = gbase + pre; g < gbase + ge.T; ++g) {
                 wait_empty(g);
                 issueA(g, cur);

@@ -117,7 +117,9 @@ int cgb_set_rhs(cgb_ctx *ctx, const double *b_host);
  * counts its launches);
  * "pdl": 0/1 programmatic dependent launch between the kernels of the iteration (the next
  * mat-vec prefetches A while the vector updates still run); "l2_prefetch": pipeline steps of A
- * the mat-vec additionally pulls into L2 before that wait (0 = off);
+ * the mat-vec additionally pulls into L2 before that wait (0 = off); "l2_ramp": persistent
+ * schedule only -- further steps pulled into L2 the moment p arrives, so that HBM keeps
+ * streaming while the steps already on chip are consumed (default 2, 0 = off);
  * "exchange": 0 ncclAllGather / 1 fused peer stores (see cgb_exchange_import);
  * "schedule": 1 (default) = the whole loop of cgb_iterate as ONE persistent cooperative kernel
  * (one CTA per SM stays resident, the iteration's dependencies are data-flow waits inside the
