@@ -175,12 +175,22 @@ int use_device(cgb_ctx *c)
     return CGB_OK;
 }
 
+// Entries that arrive in every slot of the gather buffer: the largest shard's -- or, in "loopback" (this rank
+// plays every rank of the exchange with its OWN rows: cgb_autotune, profiling), this rank's row count; reads
+// past them are clamped, else a rank with fewer rows than the last one would wait for entries nobody stores
+long long loopback_cap(const cgb_ctx *c)
+{
+    if (!c->opt_loopback) return c->maxrows > 0 ? c->maxrows : 1;
+    return c->rows > 0 ? c->rows : 1;
+}
+
 Gather make_gather(const cgb_ctx *c)
 {
     Gather g;
     g.n_loc = c->n_loc > 0 ? c->n_loc : 1;
     g.slot = c->slot;
     g.maxrows = c->maxrows;
+    g.loc_cap = loopback_cap(c);
     g.world = c->world;
     g.nblk = c->nblk;
     g.bufstride = c->bufstride;
@@ -410,6 +420,7 @@ int launch_persist(cgb_ctx *c, long long iters)
     a.n = c->n;
     a.maxrows = c->maxrows;
     a.n_loc = c->n_loc > 0 ? c->n_loc : 1;
+    a.loc_cap = loopback_cap(c);
     a.slot = c->slot;
     a.bufstride = c->bufstride;
     a.slot_off = (long long)c->rank * c->slot;

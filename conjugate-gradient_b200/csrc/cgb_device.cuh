@@ -43,6 +43,8 @@ struct Gather {
     long long n_loc;   // rows of every rank but the last (N / world)
     long long slot;    // entries per rank slot
     long long maxrows; // rows of the last rank (the largest shard)
+    long long loc_cap;   // entries that really arrive per slot: maxrows -- or, "loopback", this rank's own
+                         // row count (it plays every rank with its own rows; reads past them are clamped)
     long long bufstride; // entries per LL buffer (world * slot capacity)
     const uint4 *ll;   // this rank's LL buffers (peers write into them over NVLink)
     Ctl *ctl;
@@ -111,7 +113,7 @@ struct PersistArgs {
     Ctl *ctl;
     double *hist;              // nullable
     int *host_done;            // mapped pinned flag: 1 = converged, < 0 = a wait timed out
-    long long ld, rows, row0, n, maxrows, n_loc, slot, bufstride, slot_off, nchunks;
+    long long ld, rows, row0, n, maxrows, n_loc, loc_cap, slot, bufstride, slot_off, nchunks;
     int rank, world, iters, l2_prefetch, l2_ramp, balance;
     int scr_n;                 // shared-memory scratch: doubles for the chunk partials being summed
     double tol;
@@ -261,17 +263,18 @@ __device__ __forceinline__ void exchange_consumed(const Gather &g, int tid)
     }
 }
 
-__device__ __forceinline__ long long gather_index_raw(long long n_loc, int world, long long slot, long long i)
+__device__ __forceinline__ long long gather_index_raw(long long n_loc, int world, long long slot, long long loc_cap,
+                                                      long long i)
 {
     long long r = i / n_loc;
     if (r > world - 1) r = world - 1;
-    return r * slot + (i - r * n_loc);
+    long long l = i - r * n_loc;
+    if (l >= loc_cap) l = loc_cap - 1; // only in "loopback" (see Gather::loc_cap)
+    return r * slot + l;
 }
 __device__ __forceinline__ long long gather_index(const Gather &g, long long i)
 {
-    long long r = i / g.n_loc;
-    if (r > g.world - 1) r = g.world - 1;
-    return r * g.slot + (i - r * g.n_loc);
+    return gather_index_raw(g.n_loc, g.world, g.slot, g.loc_cap, i);
 }
 
 // Called by one full warp of block 0 before it starts streaming: nobody else touches these

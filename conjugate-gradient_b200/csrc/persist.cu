@@ -637,7 +637,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, 1) cg_persist_kernel(const Pers
                 for (int e = 0; e < EPT; ++e) {
                     const long long i = j * kChunk + tid + e * NCT;
                     const bool ok = j < a.nchunks && i < a.n;
-                    esrc[cc * EPT + e] = view + gather_index_raw(a.n_loc, a.world, a.slot, ok ? i : 0);
+                    esrc[cc * EPT + e] = view + gather_index_raw(a.n_loc, a.world, a.slot, a.loc_cap, ok ? i : 0);
                     if (ok) pending |= 1u << (cc * EPT + e);
                 }
             }

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kChunk) exchange_collect_kernel(double *apx, c
         const int r = (int)(t / per);
         const long long e = t - (long long)r * per;
         const long long rows_r = (r == g.world - 1) ? g.maxrows : g.n_loc;
-        if (e < rows_r) {
+        if (e < rows_r && e < g.loc_cap) { // loc_cap < rows_r only in "loopback"
             const long long idx = (long long)r * g.slot + e;
             apx[idx] = gather_read(gv, idx);
         }

@@ -384,6 +384,33 @@ def test_row_rebalancing_changes_no_bit(cgb, O):
             assert np.array_equal(hist, ref.hist) and np.array_equal(x, ref.x), balance
 
 
+@pytest.mark.parametrize("rank", [0, 7])
+def test_autotune_alone_on_a_ragged_shard(cgb, rank):
+    """cgb_autotune times a rank ALONE, the exchange looped back to itself.  With n % world != 0 the last
+    rank owns more rows than the others (cg.cc:236-268): a rank with fewer rows must not wait for gather
+    entries only the last rank would store (found by profiles/sanitize_small.py: 8 ranks, n = 2311, rank 0
+    sat in the wait until the spin time-out).  Both schedules, then a looped-back run of each: same bits."""
+    n = 2311
+    with cgb.Context(n, rank, 8, 0) as ctx:
+        ctx.set_option("spin_timeout_ms", 4000)
+        ctx.generate_lap2d()
+        ctx.set_rhs(cgb.init_source_term(n))
+        for schedule in (1, 0):
+            ctx.set_option("schedule", schedule)
+            res = ctx.autotune(4)
+            assert res["chosen"].startswith("tma_") and len(res["us_per_iteration"]) >= 4, res
+        ctx.set_option("loopback", 1)
+        hists = []
+        for schedule in (0, 1):
+            ctx.set_option("schedule", schedule)
+            ctx.solve_begin(None, 24, 0.0, True)
+            ctx.iterate(24)
+            hist = np.zeros(24)
+            ctx.solve_end(None, hist)
+            hists.append(hist)
+        assert np.array_equal(hists[0], hists[1], equal_nan=True)
+
+
 def test_persistent_schedule_size_limit_and_fallback(cgb, O):
     """The persistent kernel keeps the vector chunks of a CTA in registers: it takes N up to
     2 * 148 * 256 = 75776; one more and cgb_iterate falls back to the graph schedule by itself.  At
