@@ -81,8 +81,8 @@ def main():
     n = 517
     rng = np.random.default_rng(7)
     nz = 20000
-    irn = rng.integers(1, n + 1, nz).astype(np.int32)
-    jcn = rng.integers(1, n + 1, nz).astype(np.int32)
+    irn = rng.integers(0, n, nz).astype(np.int32)   # 0-based, as MatrixCOO::read hands them over
+    jcn = rng.integers(0, n, nz).astype(np.int32)
     val = rng.standard_normal(nz)
     with cgb.Context(n) as ctx:
         for sym in (False, True):

@@ -105,6 +105,22 @@ def test_multi_gpu_cli_psize_column(O, tmp_path, cgb):
     assert [row.split(",")[:2] for row in out.read_text().splitlines()] == [["2048", "2"]] * 2
 
 
+def test_multi_gpu_cli_ragged_rows(O, tmp_path, cgb):
+    """N not divisible by the GPU count: the last rank owns more rows (cg.cc:236-268).  The default path --
+    cgb_autotune on every rank alone before the timed solve, fused exchange, persistent kernel -- must
+    neither wait for rows a shorter rank never stores nor change a digit of the DEBUG line."""
+    G = cgb.device_count()
+    if G < 2:
+        pytest.skip("needs 2 GPUs")
+    n, iters = 2051, 120
+    out = tmp_path / "res.txt"
+    r = _run([str(n), str(out), str(iters)], env={"CGB_GPUS": str(G), "CGB_SPIN_TIMEOUT_MS": "5000"})
+    assert r.returncode == 0, r.stderr
+    ref = O.solve(O.generate_lap2d(n), O.init_source_term(n), max_iter=iters, nranks=G, nblk=148)
+    assert _step_line(r.stdout) == O.debug_line(iters, ref.rsold, ref.norm_x, ref.rel_resid)
+    assert out.read_text().splitlines()[0].split(",")[:2] == [str(n), str(G)]
+
+
 # --------------------------------------------------------------------------- INTEGRATION.md section B, compiled
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 REF_CGB = os.path.join(REF_DIR, "cgsolver_ref_cgb")   # the reference's main + reader + rest of cg.cc, solve -> libcgb200
