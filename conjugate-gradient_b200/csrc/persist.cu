@@ -49,12 +49,6 @@ __host__ __device__ constexpr int persist_pmax(int slot, int tc) { return slot /
 // leave 168 registers per thread): N <= 2 * 148 * 256 = 75776; larger systems take the graph schedule
 constexpr int kPersistMaxChunks = 2;
 
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
 {
     unsigned v;
@@ -64,12 +58,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
 __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v)
 {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ double ld_cg_f64(const double *p)
-{
-    double v;
-    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
 }
 __device__ __forceinline__ void fence_proxy_async_global()
 {
@@ -104,22 +92,6 @@ __device__ __noinline__ void spin_timeout(const PersistArgs &a, int what, int d0
         __threadfence_system();
     }
     __trap();
-}
-
-// One LL entry {lo, tag, hi, tag}: spin until both halves carry the tag.
-__device__ __forceinline__ double ll_wait(const PersistArgs &a, const uint4 *src, unsigned tag, uint4 v)
-{
-    if (v.y != tag || v.w != tag) {
-        const unsigned long long t0 = globaltimer_ns();
-        unsigned ns = 20;
-        do {
-            __nanosleep(ns);
-            if (ns < 320) ns += ns; // early CTAs must not hammer L2 while the others still stream
-            v = ld_volatile_v4(src);
-            if (globaltimer_ns() - t0 > a.spin_ns) spin_timeout(a, 1);
-        } while (v.y != tag || v.w != tag);
-    }
-    return __hiloint2double((int)v.z, (int)v.x);
 }
 
 // PB LL entries at once: all pending loads are in flight together in every round (polling them
